@@ -1,0 +1,1048 @@
+// hans_kernels.cu -- sm_100a kernels + C ABI of libhans_b200.so (see include/hans_b200.h).
+//
+// Execution model: one WALKER per thread group of T threads (T = 32: one warp per walker, four
+// walkers per CTA; T = 64/128/256: one CTA per walker).  The walker's beads live in shared memory
+// as float64 structure-of-arrays for the whole walk; the cell H and its inverse are kept in
+// shared memory and copied to registers around the pair loops.  All lanes of a group compute
+// the (cheap, scalar) proposal and acceptance arithmetic redundantly so control flow is uniform
+// across the group and no broadcast is needed; the O(N) / O(N^2) pair loops are split across the
+// lanes and combined with a group-wide vote that doubles as the early exit.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo  (see
+// __graft_entry__.build()).  -fmad=false is REQUIRED for bit-exact parity with the CPU checker.
+#include "hans_device.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------
+// group primitives
+// ---------------------------------------------------------------------------------------------
+template <int T> __device__ __forceinline__ void gsync()
+{
+    if (T == 32) __syncwarp(); else __syncthreads();
+}
+template <int T> __device__ __forceinline__ bool gany(bool p)
+{
+    if (T == 32) return __any_sync(FULL, p);
+    return __syncthreads_or(p ? 1 : 0) != 0;
+}
+
+// per-walker working set in shared memory
+struct WCtx {
+    int N, nb, nc, nex, npc;
+    int lane;
+    double *X, *Y, *Z;    // current beads
+    double *TX, *TY, *TZ; // trial beads (box moves)
+    double *CN;           // trial chain, [3*b + k]
+    double *SH;           // [0..8] H, [9..17] H^-1, [18..26] trial H, [27..35] trial H^-1
+    const uchar2 *itab;   // intra-chain pairs (j, b), b - j > nexclude
+    unsigned long long pairs;
+};
+
+__host__ __device__ inline int intra_pairs_per_chain(int nb, int nex)
+{
+    const int m = nb - nex - 1;
+    return m > 0 ? m * (m + 1) / 2 : 0;
+}
+
+__host__ __device__ inline size_t walker_smem_doubles(int N, int nb)
+{
+    return (size_t)6 * N + (size_t)3 * nb + 36;
+}
+
+// beads [b0, nb) of the trial chain CN against every bead of every other chain
+template <int T>
+__device__ bool chain_inter_overlap(WCtx &w, int ichain, int b0, const double *H, const double *Hi)
+{
+    const int nb = w.nb, c0 = ichain * nb, M = w.N - nb;
+    bool ov = false;
+    for (int base = 0; base < M; base += T) {
+        const int jj = base + w.lane;
+        if (jj < M) {
+            const int j = jj < c0 ? jj : jj + nb;
+            const double xj = w.X[j], yj = w.Y[j], zj = w.Z[j];
+            for (int b = b0; b < nb; ++b) {
+                const double r2 = pair_r2(H, Hi, xj - w.CN[3 * b], yj - w.CN[3 * b + 1], zj - w.CN[3 * b + 2]);
+                ov |= (r2 < 1.0);
+            }
+            w.pairs += (unsigned)(nb - b0);
+        }
+        if (gany<T>(ov)) return true;
+    }
+    return false;
+}
+
+// intra-chain pairs (j, b) of the trial chain CN with b >= b0
+template <int T>
+__device__ bool chain_intra_overlap(WCtx &w, int b0, const double *H, const double *Hi)
+{
+    bool ov = false;
+    for (int e = w.lane; e < w.npc; e += T) {
+        const uchar2 jb = w.itab[e];
+        if ((int)jb.y >= b0) {
+            const double *a = w.CN + 3 * jb.x, *b = w.CN + 3 * jb.y;
+            ov |= (pair_r2(H, Hi, b[0] - a[0], b[1] - a[1], b[2] - a[2]) < 1.0);
+            w.pairs += 1;
+        }
+    }
+    return gany<T>(ov);
+}
+
+// all inter-chain pairs (and optionally the intra-chain ones) of the beads in (X,Y,Z).
+// Chain pairs are enumerated round-robin: (ci, (ci+d) mod nc), d = 1..(nc-1)/2, plus the
+// antipodal pairs when nc is even; bead pairs inside a chain pair are nb*nb.
+template <int T>
+__device__ bool all_overlap(WCtx &w, const double *X, const double *Y, const double *Z, const double *H,
+                            const double *Hi, bool with_intra)
+{
+    const int nb = w.nb, nc = w.nc, nb2 = nb * nb;
+    const int full = nc * ((nc - 1) / 2);
+    const int ncp = nc * (nc - 1) / 2;
+    const int P = ncp * nb2;
+    bool ov = false;
+    constexpr int U = 4; // pair tests per lane between votes
+    for (int base = 0; base < P; base += T * U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = base + u * T + w.lane;
+            if (p < P) {
+                const int cp = p / nb2, r = p - cp * nb2;
+                int ci, cj;
+                if (cp < full) { const int d = cp / nc; ci = cp - d * nc; cj = ci + d + 1; if (cj >= nc) cj -= nc; }
+                else { ci = cp - full; cj = ci + nc / 2; }
+                const int bi = r / nb, bj = r - bi * nb;
+                const int i = ci * nb + bi, j = cj * nb + bj;
+                ov |= (pair_r2(H, Hi, X[j] - X[i], Y[j] - Y[i], Z[j] - Z[i]) < 1.0);
+                w.pairs += 1;
+            }
+        }
+        if (gany<T>(ov)) return true;
+    }
+    if (with_intra && w.npc > 0) {
+        const int Q = nc * w.npc;
+        for (int base = 0; base < Q; base += T) {
+            const int q = base + w.lane;
+            if (q < Q) {
+                const int ch = q / w.npc;
+                const uchar2 jb = w.itab[q - ch * w.npc];
+                const int i = ch * nb + jb.x, j = ch * nb + jb.y;
+                ov |= (pair_r2(H, Hi, X[j] - X[i], Y[j] - Y[i], Z[j] - Z[i]) < 1.0);
+                w.pairs += 1;
+            }
+        }
+        if (gany<T>(ov)) return true;
+    }
+    return false;
+}
+
+// chains follow a cell change rigidly, anchored on their first bead: (X) under Hi_old -> (TX)
+// under H_new.  src and dst may not alias.
+template <int T>
+__device__ void follow_cell(const WCtx &w, const double *sx, const double *sy, const double *sz, double *dx,
+                            double *dy, double *dz, const double *Hi_old, const double *H_new)
+{
+    for (int i = w.lane; i < w.N; i += T) {
+        const int a = (i / w.nb) * w.nb;
+        const double ax = sx[a], ay = sy[a], az = sz[a];
+        double f0, f1, f2, n0, n1, n2;
+        vecmat(ax, ay, az, Hi_old, f0, f1, f2);
+        vecmat(f0, f1, f2, H_new, n0, n1, n2);
+        dx[i] = sx[i] + (n0 - ax);
+        dy[i] = sy[i] + (n1 - ay);
+        dz[i] = sz[i] + (n2 - az);
+    }
+}
+
+template <int T> __device__ void commit_trial(WCtx &w)
+{
+    for (int i = w.lane; i < w.N; i += T) { w.X[i] = w.TX[i]; w.Y[i] = w.TY[i]; w.Z[i] = w.TZ[i]; }
+    if (w.lane < 18) w.SH[w.lane] = w.SH[18 + w.lane];
+    gsync<T>();
+}
+
+struct Dec { int accepted, reason; double boltz; };
+__device__ __forceinline__ Dec mkdec(int a, int r, double b) { Dec d; d.accepted = a; d.reason = r; d.boltz = b; return d; }
+
+// translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
+// alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
+template <int T>
+__device__ Dec move_chain(WCtx &w, const Prop &p, int mode)
+{
+    const int nb = w.nb, c0 = p.ichain * nb;
+    int b0 = 0;
+    bool intra = false;
+    if (p.type == HANS_TRANS) {
+        for (int b = w.lane; b < nb; b += T) {
+            w.CN[3 * b] = w.X[c0 + b] + p.p[0];
+            w.CN[3 * b + 1] = w.Y[c0 + b] + p.p[1];
+            w.CN[3 * b + 2] = w.Z[c0 + b] + p.p[2];
+        }
+    } else if (p.type == HANS_ROT) {
+        double com[3] = {0.0, 0.0, 0.0};
+        for (int b = 0; b < nb; ++b) { com[0] += w.X[c0 + b]; com[1] += w.Y[c0 + b]; com[2] += w.Z[c0 + b]; }
+        const double dn = (double)nb;
+        com[0] /= dn; com[1] /= dn; com[2] /= dn;
+        for (int b = w.lane; b < nb; b += T) {
+            const double v[3] = {w.X[c0 + b] - com[0], w.Y[c0 + b] - com[1], w.Z[c0 + b] - com[2]};
+            double o[3];
+            quat_rot(p.p, v, o);
+            w.CN[3 * b] = o[0] + com[0]; w.CN[3 * b + 1] = o[1] + com[1]; w.CN[3 * b + 2] = o[2] + com[2];
+        }
+    } else {
+        const int ia = p.idx0;
+        if (nb < 4 || ia < 3 || ia > nb - 1) return mkdec(0, HANS_REJ_INVALID, 0.0);
+        const bool flip = p.idx1 != 0;
+        const int iv = c0 + (flip ? nb - 1 - (ia - 1) : ia - 1);
+        const int iw = c0 + (flip ? nb - 1 - (ia - 2) : ia - 2);
+        const double piv[3] = {w.X[iv], w.Y[iv], w.Z[iv]};
+        double ax[3] = {piv[0] - w.X[iw], piv[1] - w.Y[iw], piv[2] - w.Z[iw]};
+        const double n = sqrt(dot3(ax, ax));
+        ax[0] /= n; ax[1] /= n; ax[2] /= n;
+        double s, co;
+        hd_sincos(0.5 * p.p[0], &s, &co);
+        const double q[4] = {co, s * ax[0], s * ax[1], s * ax[2]};
+        for (int b = w.lane; b < nb; b += T) {
+            const int src = c0 + (flip ? nb - 1 - b : b);
+            double r[3] = {w.X[src], w.Y[src], w.Z[src]};
+            if (b >= ia) {
+                const double v[3] = {r[0] - piv[0], r[1] - piv[1], r[2] - piv[2]};
+                double o[3];
+                quat_rot(q, v, o);
+                r[0] = o[0] + piv[0]; r[1] = o[1] + piv[1]; r[2] = o[2] + piv[2];
+            }
+            w.CN[3 * b] = r[0]; w.CN[3 * b + 1] = r[1]; w.CN[3 * b + 2] = r[2];
+        }
+        b0 = ia;
+        intra = true;
+    }
+    gsync<T>();
+    double H[9], Hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { H[k] = w.SH[k]; Hi[k] = w.SH[9 + k]; }
+    bool ov = chain_inter_overlap<T>(w, p.ichain, b0, H, Hi);
+    if (!ov && intra) ov = chain_intra_overlap<T>(w, b0, H, Hi);
+    const double boltz = ov ? 0.0 : 1.0;
+    const bool keep = (mode == HANS_MODE_PROPOSE) || (p.u_acc < boltz); // MCNS.py:372
+    if (keep) {
+        for (int b = w.lane; b < nb; b += T) {
+            w.X[c0 + b] = w.CN[3 * b]; w.Y[c0 + b] = w.CN[3 * b + 1]; w.Z[c0 + b] = w.CN[3 * b + 2];
+        }
+    }
+    gsync<T>();
+    return mkdec(ov ? 0 : 1, ov ? HANS_REJ_OVERLAP : HANS_ACCEPT, boltz);
+}
+
+// alk.alkane_box_resize(pressure, ibox, 0) + acceptance (MCNS.py:318,349-357).  The trial lives
+// in (TX,TY,TZ), so a rejection restores the saved cell and chains exactly for free.
+template <int T>
+__device__ Dec move_volume(WCtx &w, const hans_cfg &c, const Prop &p, double volume_limit, int mode)
+{
+    double H[9], Hi[9], Hn[9], Hin[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { H[k] = w.SH[k]; Hi[k] = w.SH[9 + k]; }
+    const double vol = fabs(det3(H));
+    const double vnew_t = vol + p.p[0];
+    if (!(vnew_t > 0.0)) return mkdec(0, HANS_REJ_INVALID, 0.0);
+    const double ratio = vnew_t / vol;
+    const double s = hd_cbrt(ratio);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hn[k] = H[k] * s;
+    const double new_volume = fabs(det3(Hn)); // MCNS.py:350
+    const double boltz_f = hd_exp(-c.pressure * p.p[0] + (double)c.nchains * hd_log(ratio)); // MCNS.py:266
+    if (mode == HANS_MODE_FUSED) {
+        // conjunction of MCNS.py:351 evaluated cheapest-first; the O(N^2) overlap test is last
+        if (!((new_volume - volume_limit) < 2.2204460492503131e-16)) return mkdec(0, HANS_REJ_CEILING, boltz_f);
+        if (!(p.u_acc < boltz_f)) return mkdec(0, HANS_REJ_BOLTZ, boltz_f);
+    }
+    follow_cell<T>(w, w.X, w.Y, w.Z, w.TX, w.TY, w.TZ, Hi, Hn);
+    hinv(Hn, Hin);
+    if (w.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { w.SH[18 + k] = Hn[k]; w.SH[27 + k] = Hin[k]; }
+    }
+    gsync<T>();
+    const bool ov = all_overlap<T>(w, w.TX, w.TY, w.TZ, Hn, Hin, false);
+    if (mode == HANS_MODE_PROPOSE || !ov) commit_trial<T>(w);
+    if (ov) return mkdec(0, HANS_REJ_OVERLAP, 0.0);
+    return mkdec(1, HANS_ACCEPT, boltz_f);
+}
+
+// box_shear_step (MCNS.py:135-207), box_stretch_step (MCNS.py:209-252), accept / revert by -dH
+// (MCNS.py:360-368)
+template <int T>
+__device__ Dec move_shape(WCtx &w, const hans_cfg &c, const Prop &p, int mode)
+{
+    double H[9], Hi[9], Hn[9], Hin[9], dH[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { H[k] = w.SH[k]; Hi[k] = w.SH[9 + k]; dH[k] = 0.0; }
+    if (p.type == HANS_SHEAR) {
+        const int k = p.idx0;
+        const int o0 = (k == 0) ? 1 : 0;
+        const int o1 = (k == 2) ? 1 : 2;
+        double v1[3] = {H[3 * o0], H[3 * o0 + 1], H[3 * o0 + 2]};
+        double v2[3] = {H[3 * o1], H[3 * o1 + 1], H[3 * o1 + 2]};
+        const double n1 = sqrt(dot3(v1, v1));
+        v1[0] /= n1; v1[1] /= n1; v1[2] /= n1;
+        const double pr = dot3(v1, v2);
+        v2[0] -= v1[0] * pr; v2[1] -= v1[1] * pr; v2[2] -= v1[2] * pr;
+        const double n2 = sqrt(dot3(v2, v2));
+        v2[0] /= n2; v2[1] /= n2; v2[2] /= n2;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double nw = H[3 * k + a] + (p.p[0] * v1[a] + p.p[1] * v2[a]);
+            dH[3 * k + a] = nw - H[3 * k + a];
+        }
+    } else {
+        const int i = p.idx0, j = p.idx1;
+        const double e1 = hd_exp(p.p[0]), e2 = hd_exp(-p.p[0]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dH[3 * i + a] = H[3 * i + a] * e1 - H[3 * i + a];
+            dH[3 * j + a] = H[3 * j + a] * e2 - H[3 * j + a];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hn[k] = H[k] + dH[k];
+    follow_cell<T>(w, w.X, w.Y, w.Z, w.TX, w.TY, w.TZ, Hi, Hn); // alk.alkane_change_box, MCNS.py:186,238
+    hinv(Hn, Hin);
+    if (w.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { w.SH[18 + k] = Hn[k]; w.SH[27 + k] = Hin[k]; }
+    }
+    gsync<T>();
+    int reason = HANS_ACCEPT;
+    if (min_aspect_ratio(Hn) < c.min_ar) reason = HANS_REJ_ASPECT;         // MCNS.py:194,243
+    else if (max_abs_cos(Hn) > c.cos_min_ang) reason = HANS_REJ_ANGLE;     // MCNS.py:196,245
+    else if (all_overlap<T>(w, w.TX, w.TY, w.TZ, Hn, Hin, true)) reason = HANS_REJ_OVERLAP; // MCNS.py:198,247
+    if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
+        commit_trial<T>(w);
+    } else {
+        // MCNS.py:366-368: the reference reverts by applying -dH through alkane_change_box, which
+        // is not an exact restore; reproduce that arithmetic from the trial state.
+        double H2[9], H2i[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H2[k] = Hn[k] + (-1.0 * dH[k]);
+        follow_cell<T>(w, w.TX, w.TY, w.TZ, w.X, w.Y, w.Z, Hin, H2);
+        hinv(H2, H2i);
+        if (w.lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { w.SH[k] = H2[k]; w.SH[9 + k] = H2i[k]; }
+        }
+        gsync<T>();
+    }
+    return mkdec(reason == HANS_ACCEPT ? 1 : 0, reason, reason == HANS_ACCEPT ? 1.0 : 0.0);
+}
+
+template <int T>
+__device__ __forceinline__ Dec apply_move(WCtx &w, const hans_cfg &c, const Prop &p, double volume_limit, int mode)
+{
+    if (p.type == HANS_VOL) return move_volume<T>(w, c, p, volume_limit, mode);
+    if (p.type <= HANS_DIH) return move_chain<T>(w, p, mode);
+    return move_shape<T>(w, c, p, mode);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory carve-up and state load/store
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ void setup_ctx(WCtx &w, const hans_cfg &c, double *smem, int groups_per_cta)
+{
+    w.nb = c.nbeads; w.nc = c.nchains; w.N = c.nbeads * c.nchains; w.nex = c.nexclude;
+    w.npc = intra_pairs_per_chain(w.nb, w.nex);
+    w.lane = threadIdx.x % T;
+    const int g = threadIdx.x / T;
+    const size_t per = walker_smem_doubles(w.N, w.nb);
+    double *base = smem + per * g;
+    w.X = base; w.Y = w.X + w.N; w.Z = w.Y + w.N;
+    w.TX = w.Z + w.N; w.TY = w.TX + w.N; w.TZ = w.TY + w.N;
+    w.CN = w.TZ + w.N;
+    w.SH = w.CN + 3 * w.nb;
+    uchar2 *tab = reinterpret_cast<uchar2 *>(smem + per * groups_per_cta);
+    w.itab = tab;
+    w.pairs = 0;
+    // intra-chain pair table, ordered by b then j (one per CTA)
+    for (int e = threadIdx.x; e < w.npc; e += blockDim.x) {
+        int b = w.nex + 1, acc = 0;
+        while (acc + (b - w.nex) <= e) { acc += b - w.nex; ++b; }
+        tab[e] = make_uchar2((unsigned char)(e - acc), (unsigned char)b);
+    }
+    __syncthreads();
+}
+
+template <int T>
+__device__ void load_walker(WCtx &w, const double *gH, const double *gR, int wi)
+{
+    const double *r = gR + (size_t)wi * w.N * 3;
+    for (int i = w.lane; i < w.N; i += T) { w.X[i] = r[3 * i]; w.Y[i] = r[3 * i + 1]; w.Z[i] = r[3 * i + 2]; }
+    double H[9], Hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = gH[(size_t)wi * 9 + k];
+    hinv(H, Hi);
+    if (w.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { w.SH[k] = H[k]; w.SH[9 + k] = Hi[k]; }
+    }
+    gsync<T>();
+}
+
+template <int T>
+__device__ void store_walker(const WCtx &w, double *gH, double *gR, int wi)
+{
+    double *r = gR + (size_t)wi * w.N * 3;
+    for (int i = w.lane; i < w.N; i += T) { r[3 * i] = w.X[i]; r[3 * i + 1] = w.Y[i]; r[3 * i + 2] = w.Z[i]; }
+    if (w.lane < 9) gH[(size_t)wi * 9 + w.lane] = w.SH[w.lane];
+}
+
+template <int T> __device__ void flush_pairs(WCtx &w, unsigned long long *g_pairs)
+{
+    if (g_pairs == nullptr) return;
+    unsigned long long v = w.pairs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(g_pairs, v);
+    w.pairs = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+struct WalkArgs {
+    hans_cfg cfg;
+    double *H, *R;
+    unsigned long long *ctr;
+    const int32_t *ids;
+    int n_active, nmoves;
+    const double *d_limit;
+    double limit;
+    unsigned long long seed;
+    uint32_t gid_base;
+    unsigned long long *attempted, *accepted;
+    double *vol;
+    unsigned long long *pair_tests;
+    // replay
+    const hans_proposal *props;
+    hans_decision *out;
+    int mode;
+};
+
+template <int T> __host__ __device__ constexpr int cta_threads() { return T == 32 ? 128 : T; }
+
+// MC_run (MCNS.py:276-392) for a batch of walkers; REPLAY = proposals come from memory
+template <int T, bool REPLAY>
+__global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a)
+{
+    extern __shared__ double smem[];
+    constexpr int GPC = cta_threads<T>() / T;
+    WCtx w;
+    setup_ctx<T>(w, a.cfg, smem, GPC);
+    const int g = threadIdx.x / T;
+    const double limit = a.d_limit ? *a.d_limit : a.limit;
+    // n_active rounded up so that every group of a CTA runs the same number of iterations
+    for (int k0 = blockIdx.x * GPC; k0 < a.n_active; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < a.n_active) {
+            const int wi = a.ids ? a.ids[k] : k;
+            load_walker<T>(w, a.H, a.R, wi);
+            const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
+            unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
+            for (int m = 0; m < a.nmoves; ++m) {
+                Prop p;
+                if (REPLAY) {
+                    const hans_proposal *q = a.props + (size_t)k * a.nmoves + m;
+                    p.type = q->type; p.ichain = q->ichain; p.idx0 = q->idx0; p.idx1 = q->idx1;
+                    p.p[0] = q->p[0]; p.p[1] = q->p[1]; p.p[2] = q->p[2]; p.p[3] = q->p[3];
+                    p.u_acc = q->u_acc;
+                } else {
+                    p = gen_proposal(a.cfg, a.seed, a.gid_base + (uint32_t)wi, ctr0 + (unsigned long long)m);
+                }
+                const Dec d = apply_move<T>(w, a.cfg, p, limit, a.mode);
+#pragma unroll
+                for (int t = 0; t < 6; ++t) { att[t] += (p.type == t); acc[t] += (p.type == t && d.accepted); }
+                if (REPLAY && w.lane == 0) {
+                    hans_decision *o = a.out + (size_t)k * a.nmoves + m;
+                    o->accepted = d.accepted; o->reason = d.reason; o->boltz = d.boltz;
+                }
+            }
+            store_walker<T>(w, a.H, a.R, wi);
+            if (w.lane == 0) {
+                if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
+                if (a.vol) a.vol[wi] = fabs(det3(w.SH));
+                if (a.attempted) {
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) { a.attempted[(size_t)k * 6 + t] += att[t]; a.accepted[(size_t)k * 6 + t] += acc[t]; }
+                }
+            }
+            flush_pairs<T>(w, a.pair_tests);
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// alk.alkane_check_chain_overlap (MCNS.py:198,247,543) for a batch of walkers
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+overlap_kernel(const hans_cfg cfg, const double *gH, const double *gR, const int32_t *ids, int n, int inter_only,
+               int32_t *out)
+{
+    extern __shared__ double smem[];
+    constexpr int GPC = cta_threads<T>() / T;
+    WCtx w;
+    setup_ctx<T>(w, cfg, smem, GPC);
+    const int g = threadIdx.x / T;
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            load_walker<T>(w, gH, gR, wi);
+            double H[9], Hi[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { H[q] = w.SH[q]; Hi[q] = w.SH[9 + q]; }
+            const bool ov = all_overlap<T>(w, w.X, w.Y, w.Z, H, Hi, !inter_only);
+            if (w.lane == 0) out[k] = ov ? 1 : 0;
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// alk.alkane_change_box(ibox, dH) (MCNS.py:186,238,368) for a batch of walkers
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+change_box_kernel(const hans_cfg cfg, double *gH, double *gR, const int32_t *ids, int n, const double *gdH)
+{
+    extern __shared__ double smem[];
+    constexpr int GPC = cta_threads<T>() / T;
+    WCtx w;
+    setup_ctx<T>(w, cfg, smem, GPC);
+    const int g = threadIdx.x / T;
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            load_walker<T>(w, gH, gR, wi);
+            double Hi[9], Hn[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { Hi[q] = w.SH[9 + q]; Hn[q] = w.SH[q] + gdH[(size_t)k * 9 + q]; }
+            follow_cell<T>(w, w.X, w.Y, w.Z, w.TX, w.TY, w.TZ, Hi, Hn);
+            gsync<T>();
+            if (w.lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) w.SH[18 + q] = Hn[q];
+            }
+            gsync<T>();
+            commit_trial<T>(w);
+            store_walker<T>(w, gH, gR, wi);
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// create_initial_configs / populate_boxes (MCNS.py:628-644); alk.alkane_grow_chain (MCNS.py:642).
+// Random insertion with fixed bond length / angle and uniform dihedrals; a chain is retried with
+// the next attempt counter until it overlaps nothing already placed.
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+grow_kernel(const hans_cfg cfg, const double *gH, double *gR, const int32_t *ids, int n, unsigned long long seed,
+            uint32_t gid_base, const uint32_t *gid_override, int chain_begin, int chain_end, uint32_t attempt_begin,
+            int max_attempts, int32_t *status)
+{
+    extern __shared__ double smem[];
+    constexpr int GPC = cta_threads<T>() / T;
+    WCtx w;
+    setup_ctx<T>(w, cfg, smem, GPC);
+    const int g = threadIdx.x / T;
+    const int nb = w.nb;
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            const uint32_t gid = gid_override ? gid_override[k] : gid_base + (uint32_t)wi;
+            load_walker<T>(w, gH, gR, wi);
+            double H[9], Hi[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { H[q] = w.SH[q]; Hi[q] = w.SH[9 + q]; }
+            const int cend = chain_end < 0 ? w.nc : chain_end;
+            int total = 0;
+            bool failed = false;
+            for (int ic = chain_begin; ic < cend && !failed; ++ic) {
+                bool placed = false;
+                for (int at = 0; at < max_attempts && !placed; ++at) {
+                    ++total;
+                    const uint32_t attempt = attempt_begin + (uint32_t)at;
+                    // every lane builds the same trial chain; uniforms u[0..nb+2]
+                    double ua, ub, uc, ud, ue, uf;
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 0u, STREAM_GROW, ua, ub);
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 1u, STREAM_GROW, uc, ud);
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 2u, STREAM_GROW, ue, uf);
+                    double x0, y0, z0;
+                    vecmat(ua, ub, uc, H, x0, y0, z0);
+                    double pp[3] = {x0, y0, z0}, pc[3] = {x0, y0, z0}; // previous-previous, previous
+                    if (w.lane == 0) { w.CN[0] = x0; w.CN[1] = y0; w.CN[2] = z0; }
+                    if (nb > 1) {
+                        const double z = 2.0 * ud - 1.0;
+                        const double st2 = 1.0 - z * z;
+                        const double st = sqrt(st2 > 0.0 ? st2 : 0.0);
+                        double s, co;
+                        hd_sincos(HD_TWO_PI * ue, &s, &co);
+                        pc[0] = x0 + cfg.bondlength * (st * co);
+                        pc[1] = y0 + cfg.bondlength * (st * s);
+                        pc[2] = z0 + cfg.bondlength * z;
+                        if (w.lane == 0) { w.CN[3] = pc[0]; w.CN[4] = pc[1]; w.CN[5] = pc[2]; }
+                    }
+                    double ucur_a = ue, ucur_b = uf; // block 2 holds u[4], u[5]
+                    uint32_t cur_blk = 2u;
+                    for (int kb = 2; kb < nb; ++kb) {
+                        const int ui = 5 + (kb - 2); // index of the uniform for this bead
+                        const uint32_t blk = (uint32_t)(ui >> 1);
+                        if (blk != cur_blk) { draw_block(seed, attempt, (uint32_t)ic, gid, blk, STREAM_GROW, ucur_a, ucur_b); cur_blk = blk; }
+                        const double u = (ui & 1) ? ucur_b : ucur_a;
+                        const double b[3] = {pc[0] - pp[0], pc[1] - pp[1], pc[2] - pp[2]};
+                        const double bn = sqrt(dot3(b, b));
+                        const double uh[3] = {b[0] / bn, b[1] / bn, b[2] / bn};
+                        int ax = 0;
+                        if (fabs(uh[1]) < fabs(uh[ax])) ax = 1;
+                        if (fabs(uh[2]) < fabs(uh[ax])) ax = 2;
+                        double e[3] = {0.0, 0.0, 0.0}, e1[3], e2[3];
+                        e[ax] = 1.0;
+                        cross3(uh, e, e1);
+                        const double n1 = sqrt(dot3(e1, e1));
+                        e1[0] /= n1; e1[1] /= n1; e1[2] /= n1;
+                        cross3(uh, e1, e2);
+                        double s, co;
+                        hd_sincos(HD_TWO_PI * u, &s, &co);
+                        double nw[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const double nd = -cfg.cos_bondangle * uh[q] + cfg.sin_bondangle * (co * e1[q] + s * e2[q]);
+                            nw[q] = pc[q] + cfg.bondlength * nd;
+                        }
+                        if (w.lane == 0) { w.CN[3 * kb] = nw[0]; w.CN[3 * kb + 1] = nw[1]; w.CN[3 * kb + 2] = nw[2]; }
+                        pp[0] = pc[0]; pp[1] = pc[1]; pp[2] = pc[2];
+                        pc[0] = nw[0]; pc[1] = nw[1]; pc[2] = nw[2];
+                    }
+                    gsync<T>();
+                    // against everything already placed (chains < ic), then intra-chain
+                    bool ov = false;
+                    const int M = ic * nb;
+                    for (int base = 0; base < M; base += T) {
+                        const int j = base + w.lane;
+                        if (j < M) {
+                            const double xj = w.X[j], yj = w.Y[j], zj = w.Z[j];
+                            for (int b = 0; b < nb; ++b)
+                                ov |= (pair_r2(H, Hi, xj - w.CN[3 * b], yj - w.CN[3 * b + 1], zj - w.CN[3 * b + 2]) < 1.0);
+                        }
+                        if (gany<T>(ov)) break;
+                    }
+                    ov = gany<T>(ov);
+                    if (!ov) ov = chain_intra_overlap<T>(w, 0, H, Hi);
+                    if (!ov) {
+                        for (int b = w.lane; b < nb; b += T) {
+                            w.X[ic * nb + b] = w.CN[3 * b]; w.Y[ic * nb + b] = w.CN[3 * b + 1]; w.Z[ic * nb + b] = w.CN[3 * b + 2];
+                        }
+                        placed = true;
+                    }
+                    gsync<T>();
+                }
+                if (!placed) failed = true;
+            }
+            store_walker<T>(w, const_cast<double *>(gH), gR, wi);
+            if (w.lane == 0 && status) status[k] = failed ? -1 : total;
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// alk.box_compute_volume / box_min_aspect_ratio / min_angle (MCNS.py:97-133) for n cells
+__global__ void metrics_kernel(const double *gH, int n, double *vol, double *mar, double *mcos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double H[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = gH[(size_t)i * 9 + k];
+    if (vol) vol[i] = fabs(det3(H));
+    if (mar) mar[i] = min_aspect_ratio(H);
+    if (mcos) mcos[i] = max_abs_cos(H);
+}
+
+// local MAXLOC (mpihans.py:211-212): ties -> lowest index
+__global__ void argmax_kernel(const double *vol, int n, double *out2)
+{
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    double best = -1.7976931348623157e308;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = vol[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(FULL, best, o);
+        const int oi = __shfl_down_sync(FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        best = threadIdx.x < nw ? sv[threadIdx.x] : -1.7976931348623157e308;
+        bi = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(FULL, best, o);
+            const int oi = __shfl_down_sync(FULL, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { out2[0] = best; out2[1] = (double)bi; }
+    }
+}
+
+// clone (mpihans.py:226-237)
+__global__ void clone_kernel(int N, const double *sH, const double *sR, const double *svol, int src,
+                             const int32_t *d_src, double *dH, double *dR, double *dvol, int dst,
+                             const int32_t *d_dst, const int32_t *d_enable)
+{
+    if (d_enable && *d_enable == 0) return;
+    const int s = d_src ? *d_src : src;
+    const int d = d_dst ? *d_dst : dst;
+    const double *r = sR + (size_t)s * N * 3;
+    double *o = dR + (size_t)d * N * 3;
+    if (r == o) return;
+    for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) o[i] = r[i];
+    if (threadIdx.x < 9) dH[(size_t)d * 9 + threadIdx.x] = sH[(size_t)s * 9 + threadIdx.x];
+    if (threadIdx.x == 0 && dvol && svol) dvol[d] = svol[s];
+}
+
+// FP32 FFMA issue-rate probe (roofline denominator)
+__global__ void ffma_kernel(int iters, float *sink)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+    }
+    const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123456.789f) sink[0] = s;
+}
+
+} // namespace hb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace hb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(HANS_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+static int check_cfg(const hans_cfg *c)
+{
+    if (!c) return fail(HANS_EINVAL, "cfg is NULL");
+    if (c->nchains < 1 || c->nbeads < 1) return fail(HANS_EINVAL, "nchains and nbeads must be >= 1");
+    if (c->nbeads > HANS_MAX_BEADS) return fail(HANS_ELIMIT, "nbeads exceeds HANS_MAX_BEADS");
+    if (c->nchains > 32767) return fail(HANS_ELIMIT, "nchains too large");
+    if (c->nexclude < 0) return fail(HANS_EINVAL, "nexclude must be >= 0");
+    return HANS_OK;
+}
+
+static size_t cta_smem_bytes(const hans_cfg *c, int T)
+{
+    const int gpc = (T == 32) ? 4 : 1;
+    const int N = c->nchains * c->nbeads;
+    size_t b = walker_smem_doubles(N, c->nbeads) * sizeof(double) * gpc;
+    b += (size_t)intra_pairs_per_chain(c->nbeads, c->nexclude) * sizeof(uchar2);
+    return (b + 15) & ~(size_t)15;
+}
+
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+template <typename K> static int prep_kernel(K kernel, size_t smem)
+{
+    if (smem > 227 * 1024) return fail(HANS_ELIMIT, "walker does not fit in shared memory (cell-list path not built yet)");
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return HANS_OK;
+}
+
+static int grid_for(int n, int T)
+{
+    const int gpc = (T == 32) ? 4 : 1;
+    const int ctas = (n + gpc - 1) / gpc;
+    const int cap = sm_count() * 16;
+    return ctas < cap ? (ctas > 0 ? ctas : 1) : cap;
+}
+
+static int pick_T(const hans_cfg *c, int T)
+{
+    if (T == 0) T = hans_default_threads_per_walker(c);
+    if (T != 32 && T != 64 && T != 128 && T != 256) return -1;
+    return T;
+}
+
+#define DISPATCH_T(T, ...)                                    \
+    switch (T) {                                              \
+    case 32: { constexpr int TT = 32; __VA_ARGS__; } break;   \
+    case 64: { constexpr int TT = 64; __VA_ARGS__; } break;   \
+    case 128: { constexpr int TT = 128; __VA_ARGS__; } break; \
+    default: { constexpr int TT = 256; __VA_ARGS__; } break;  \
+    }
+
+extern "C" {
+
+int hans_abi_version(void) { return HANS_ABI_VERSION; }
+const char *hans_last_error(void) { return g_err.c_str(); }
+
+int hans_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t hans_walker_smem_bytes(const hans_cfg *cfg)
+{
+    if (check_cfg(cfg) != HANS_OK) return -1;
+    return (int64_t)(walker_smem_doubles(cfg->nchains * cfg->nbeads, cfg->nbeads) * sizeof(double));
+}
+
+int hans_moves_per_sweep(int nbeads, int nchains)
+{
+    if (nbeads == 1) return nchains + 7;
+    if (nbeads <= 3) return 2 * nchains + 7;
+    return (nbeads - 1) * nchains + 7;
+}
+
+int hans_default_threads_per_walker(const hans_cfg *cfg)
+{
+    if (!cfg) return 32;
+    const int N = cfg->nchains * cfg->nbeads;
+    if (N <= 128) return 32;
+    if (N <= 256) return 64;
+    if (N <= 512) return 128;
+    return 256;
+}
+
+int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
+                      int n_active, int sweeps, const double *d_volume_limit, double volume_limit, uint64_t seed,
+                      uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted, double *d_vol,
+                      uint64_t *d_pair_tests, int threads_per_walker, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R || !d_ctr) return fail(HANS_EINVAL, "d_H, d_R and d_ctr are required");
+    if (n_active < 0 || sweeps < 0) return fail(HANS_EINVAL, "negative n_active / sweeps");
+    if ((d_attempted == nullptr) != (d_accepted == nullptr)) return fail(HANS_EINVAL, "d_attempted and d_accepted go together");
+    if (n_active == 0) return HANS_OK;
+    const int T = pick_T(cfg, threads_per_walker);
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 32, 64, 128 or 256");
+    WalkArgs a;
+    memset(&a, 0, sizeof a);
+    a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ctr = (unsigned long long *)d_ctr; a.ids = d_ids; a.n_active = n_active;
+    a.nmoves = sweeps * hans_moves_per_sweep(cfg->nbeads, cfg->nchains);
+    a.d_limit = d_volume_limit; a.limit = volume_limit; a.seed = seed; a.gid_base = gid_base;
+    a.attempted = (unsigned long long *)d_attempted; a.accepted = (unsigned long long *)d_accepted;
+    a.vol = d_vol; a.pair_tests = (unsigned long long *)d_pair_tests; a.mode = HANS_MODE_FUSED;
+    const size_t smem = cta_smem_bytes(cfg, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        rc = prep_kernel(walk_kernel<TT, false>, smem);
+        if (rc) return rc;
+        walk_kernel<TT, false><<<grid_for(n_active, TT), cta_threads<TT>(), smem, st>>>(a);
+    });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n_active,
+                const hans_proposal *d_props, int nmoves, double volume_limit, int mode, hans_decision *d_out,
+                int threads_per_walker, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R || !d_props || !d_out) return fail(HANS_EINVAL, "NULL device pointer");
+    if (mode != HANS_MODE_FUSED && mode != HANS_MODE_PROPOSE) return fail(HANS_EINVAL, "bad mode");
+    if (n_active < 0 || nmoves < 0) return fail(HANS_EINVAL, "negative count");
+    if (n_active == 0 || nmoves == 0) return HANS_OK;
+    const int T = pick_T(cfg, threads_per_walker);
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 32, 64, 128 or 256");
+    WalkArgs a;
+    memset(&a, 0, sizeof a);
+    a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ids = d_ids; a.n_active = n_active; a.nmoves = nmoves;
+    a.limit = volume_limit; a.props = d_props; a.out = d_out; a.mode = mode;
+    const size_t smem = cta_smem_bytes(cfg, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        rc = prep_kernel(walk_kernel<TT, true>, smem);
+        if (rc) return rc;
+        walk_kernel<TT, true><<<grid_for(n_active, TT), cta_threads<TT>(), smem, st>>>(a);
+    });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_check_overlap(const hans_cfg *cfg, const double *d_H, const double *d_R, const int32_t *d_ids, int n,
+                       int inter_only, int32_t *d_out, int threads_per_walker, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R || !d_out) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 0) return fail(HANS_EINVAL, "negative count");
+    if (n == 0) return HANS_OK;
+    const int T = pick_T(cfg, threads_per_walker);
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 32, 64, 128 or 256");
+    const size_t smem = cta_smem_bytes(cfg, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        rc = prep_kernel(overlap_kernel<TT>, smem);
+        if (rc) return rc;
+        overlap_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, inter_only, d_out);
+    });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_cell_metrics(const double *d_H, int n, double *d_vol, double *d_min_ar, double *d_max_cos, void *stream)
+{
+    if (!d_H) return fail(HANS_EINVAL, "d_H is NULL");
+    if (n < 0) return fail(HANS_EINVAL, "negative count");
+    if (n == 0) return HANS_OK;
+    metrics_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_H, n, d_vol, d_min_ar, d_max_cos);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_change_box(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n, const double *d_dH,
+                    void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R || !d_dH) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 0) return fail(HANS_EINVAL, "negative count");
+    if (n == 0) return HANS_OK;
+    const int T = pick_T(cfg, 0);
+    const size_t smem = cta_smem_bytes(cfg, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(T, {
+        rc = prep_kernel(change_box_kernel<TT>, smem);
+        if (rc) return rc;
+        change_box_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, d_dH);
+    });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+static int launch_grow(const hans_cfg *cfg, const double *d_H, double *d_R, const int32_t *d_ids, int n, uint64_t seed,
+                       uint32_t gid_base, const uint32_t *d_gid, int cb, int ce, uint32_t attempt0, int max_attempts,
+                       int32_t *d_status, void *stream)
+{
+    const int T = pick_T(cfg, 0);
+    const size_t smem = cta_smem_bytes(cfg, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = HANS_OK;
+    DISPATCH_T(T, {
+        rc = prep_kernel(grow_kernel<TT>, smem);
+        if (rc) return rc;
+        grow_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, seed, gid_base, d_gid,
+                                                                          cb, ce, attempt0, max_attempts, d_status);
+    });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_grow(const hans_cfg *cfg, const double *d_H, double *d_R, int n, uint64_t seed, uint32_t gid_base,
+              int max_attempts, int32_t *d_status, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 0 || max_attempts < 1) return fail(HANS_EINVAL, "bad count");
+    if (n == 0) return HANS_OK;
+    return launch_grow(cfg, d_H, d_R, nullptr, n, seed, gid_base, nullptr, 0, -1, 0u, max_attempts, d_status, stream);
+}
+
+int hans_grow_chain(const hans_cfg *cfg, const double *d_H, double *d_R, int walker, int ichain, uint64_t seed,
+                    uint32_t gid, uint32_t attempt, int32_t *d_ifail, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R || !d_ifail) return fail(HANS_EINVAL, "NULL device pointer");
+    if (walker < 0 || ichain < 0 || ichain >= cfg->nchains) return fail(HANS_EINVAL, "bad walker / chain index");
+    // one walker, one chain, one attempt: status = 1 (attempts used) on success, -1 on failure
+    const size_t off_h = (size_t)walker * 9, off_r = (size_t)walker * cfg->nchains * cfg->nbeads * 3;
+    // gid is passed through gid_base with walker index 0 of the shifted views
+    return launch_grow(cfg, d_H + off_h, d_R + off_r, nullptr, 1, seed, gid, nullptr, ichain, ichain + 1, attempt, 1,
+                       d_ifail, stream);
+}
+
+int hans_argmax(const double *d_vol, int n, double *d_out2, void *stream)
+{
+    if (!d_vol || !d_out2) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 1) return fail(HANS_EINVAL, "n must be >= 1");
+    argmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_vol, n, d_out2);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_clone(const hans_cfg *cfg, const double *d_srcH, const double *d_srcR, const double *d_srcvol, int src,
+               const int32_t *d_src_index, double *d_dstH, double *d_dstR, double *d_dstvol, int dst,
+               const int32_t *d_dst_index, const int32_t *d_enable, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_srcH || !d_srcR || !d_dstH || !d_dstR) return fail(HANS_EINVAL, "NULL device pointer");
+    if (src < 0 || dst < 0) return fail(HANS_EINVAL, "negative walker index");
+    clone_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(cfg->nchains * cfg->nbeads, d_srcH, d_srcR, d_srcvol, src, d_src_index,
+                                                      d_dstH, d_dstR, d_dstvol, dst, d_dst_index, d_enable);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_ffma_peak(int iters, double *tflops, void *stream)
+{
+    if (!tflops || iters < 1) return fail(HANS_EINVAL, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *sink = nullptr;
+    CK(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = sm_count() * 8, threads = 256;
+    ffma_kernel<<<blocks, threads, 0, st>>>(iters, sink); // warm-up
+    CK(cudaEventRecord(e0, st));
+    ffma_kernel<<<blocks, threads, 0, st>>>(iters, sink);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return HANS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,182 @@
+/*
+ * hans_b200.h -- C ABI of libhans_b200.so, the B200 (sm_100a) replacement for the box / chain /
+ * overlap entry points of hs_alkane that hans' nested-sampling walker engine calls
+ * (import at /root/reference/NesSa/MCNS.py:2; call sites listed per function below).
+ *
+ * Boundary rules
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types.
+ *   - every pointer named d_* is a DEVICE pointer (the Python host layer allocates them as torch
+ *     CUDA tensors and passes .data_ptr()); pointers without the prefix are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued asynchronously on it, nothing synchronises unless stated.
+ *   - every entry returns 0 on success, a negative HANS_E* code otherwise (never exits);
+ *     hans_last_error() gives the text.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns HANS_ECUDA.
+ *
+ * State layout (float64, identical to what the reference stores in restart.hdf5,
+ * NSio.py:86-95): for walker w of a pool,
+ *     d_H[w*9 .. w*9+8]            3x3 cell, rows = cell vectors (MCNS.py:112-113)
+ *     d_R[(w*N + i)*3 .. +2]       Cartesian bead i = ichain*nbeads + ibead, N = nchains*nbeads
+ *     d_ctr[w]                     number of trial moves this walker has consumed (Philox counter)
+ *     d_vol[w]                     |det H| as of the walker's last walk
+ * Indices are 0-based in this ABI; the Python shim converts from the reference's 1-based ibox /
+ * ichain.
+ */
+#ifndef HANS_B200_H
+#define HANS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HANS_ABI_VERSION 1
+
+enum { HANS_OK = 0, HANS_EINVAL = -1, HANS_ECUDA = -2, HANS_ELIMIT = -3 };
+
+/* move types, order of move_ratio (MCNS.py:25-27) */
+enum { HANS_VOL = 0, HANS_TRANS = 1, HANS_ROT = 2, HANS_DIH = 3, HANS_SHEAR = 4, HANS_STRETCH = 5 };
+
+/* decision reasons */
+enum {
+    HANS_ACCEPT = 0,
+    HANS_REJ_OVERLAP = 1,
+    HANS_REJ_CEILING = 2,
+    HANS_REJ_BOLTZ = 3,
+    HANS_REJ_ASPECT = 4,
+    HANS_REJ_ANGLE = 5,
+    HANS_REJ_INVALID = 6
+};
+
+enum {
+    HANS_MODE_FUSED = 0,  /* MC_run semantics (MCNS.py:349-380): decide, revert on reject */
+    HANS_MODE_PROPOSE = 1 /* hs_alkane entry-point semantics: leave trial state, return boltz */
+};
+
+#define HANS_MAX_BEADS 64 /* beads per chain */
+
+/* Model + move parameters.  Replaces hs_alkane's module state set through
+ * alkane_set_nchains/nbeads/bondlength/bondangle, alkane_set_d{v,r,t,h}_max (MCNS.py:599-606,
+ * mpihans.py:118-133) and the MC_run arguments (MCNS.py:276-277). */
+typedef struct hans_cfg {
+    int32_t nchains;
+    int32_t nbeads;
+    int32_t nexclude;   /* intra-chain pairs tested iff |i-j| > nexclude (default 3) */
+    int32_t allow_flip; /* alkane_bond_rotate(.., allow_flip), MCNS.py:333 */
+    double dv_max, dr_max, dt_max, dh_max, dshear, dstretch;
+    double min_ar;      /* MCNS.py:194,243 */
+    double cos_min_ang; /* cos(min_ang in radians), MCNS.py:190-196 */
+    double pressure;    /* MCNS.py:277 */
+    double move_cum[6]; /* cumsum(move_ratio)/sum, MCNS.py:294 */
+    double bondlength;  /* alkane_set_bondlength, MCNS.py:605 */
+    double cos_bondangle, sin_bondangle; /* alkane_set_bondangle, MCNS.py:606 */
+} hans_cfg;
+
+/* One explicit trial move (replay mode). */
+typedef struct hans_proposal {
+    int32_t type;
+    int32_t ichain;
+    int32_t idx0; /* dih: first rotated bead | shear: k | stretch: i */
+    int32_t idx1; /* dih: flip | stretch: j */
+    double p[4];  /* vol: dV | trans: dr[3] | rot: quaternion wxyz | dih: angle | shear: rv1,rv2 |
+                     stretch: rv */
+    double u_acc;
+    double reserved;
+} hans_proposal;
+
+typedef struct hans_decision {
+    int32_t accepted;
+    int32_t reason;
+    double boltz;
+} hans_decision;
+
+int hans_abi_version(void);
+const char *hans_last_error(void);
+/* number of CUDA devices visible (0 if none / no driver); never fails */
+int hans_device_count(void);
+/* shared memory bytes one walker needs; lets the host pick threads_per_walker */
+int64_t hans_walker_smem_bytes(const hans_cfg *cfg);
+/* MCNS.py:296-301 */
+int hans_moves_per_sweep(int nbeads, int nchains);
+/* default threads per walker for a shape (32 = one warp per walker, else one CTA per walker) */
+int hans_default_threads_per_walker(const hans_cfg *cfg);
+
+/* ---- the fused hot path ---------------------------------------------------------------------
+ * MC_run (NesSa/MCNS.py:276-392) for n_active walkers at once: sweeps * moves_per_sweep trial
+ * moves each, proposals drawn from Philox4x32-10 keyed by (seed; d_ctr[w], gid_base + w).
+ * d_ids[n_active]     walkers to walk (NULL = walkers 0..n_active-1)
+ * d_volume_limit      device scalar with the volume ceiling (NULL = use volume_limit)
+ * d_attempted/d_accepted  [n_active][6] counters, ACCUMULATED into (may be NULL)
+ * d_vol               [pool] volumes, entry w rewritten for every walked w (may be NULL)
+ * d_pair_tests        device scalar, executed pair tests accumulated (may be NULL)
+ * threads_per_walker  32, 64, 128 or 256; 0 = hans_default_threads_per_walker
+ * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
+int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
+                      const int32_t *d_ids, int n_active, int sweeps,
+                      const double *d_volume_limit, double volume_limit, uint64_t seed,
+                      uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted,
+                      double *d_vol, uint64_t *d_pair_tests, int threads_per_walker, void *stream);
+
+/* ---- replay: explicit proposals in, decisions out (bit-exact parity entry) -------------------
+ * d_props[n_active][nmoves], d_out[n_active][nmoves].  mode = HANS_MODE_FUSED | HANS_MODE_PROPOSE.
+ * With HANS_MODE_PROPOSE and nmoves = 1 this IS alk.alkane_translate_chain / alkane_rotate_chain /
+ * alkane_bond_rotate / alkane_box_resize(..,0) / box_shear_step / box_stretch_step
+ * (MCNS.py:318-343): the trial state is left in place and boltz is returned. */
+int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n_active,
+                const hans_proposal *d_props, int nmoves, double volume_limit, int mode,
+                hans_decision *d_out, int threads_per_walker, void *stream);
+
+/* ---- predicates -----------------------------------------------------------------------------
+ * alk.alkane_check_chain_overlap (MCNS.py:198,247,543) for n walkers: d_out[k] = 1 if any two
+ * beads of different chains (and, unless inter_only, non-excluded beads of one chain) are closer
+ * than sigma = 1 under the minimum image convention. */
+int hans_check_overlap(const hans_cfg *cfg, const double *d_H, const double *d_R,
+                       const int32_t *d_ids, int n, int inter_only, int32_t *d_out,
+                       int threads_per_walker, void *stream);
+
+/* alk.box_compute_volume, alk.box_min_aspect_ratio (MCNS.py:97-118,194) and the largest |cos|
+ * between cell vectors (min_angle = arccos of it, MCNS.py:120-133) for n cells; any output may be
+ * NULL. */
+int hans_cell_metrics(const double *d_H, int n, double *d_vol, double *d_min_ar, double *d_max_cos,
+                      void *stream);
+
+/* alk.alkane_change_box(ibox, dH) (MCNS.py:186,238,368): H += dH, chains follow rigidly.
+ * d_dH[n][9]. */
+int hans_change_box(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n,
+                    const double *d_dH, void *stream);
+
+/* ---- initial configurations -------------------------------------------------------------------
+ * create_initial_configs + populate_boxes (MCNS.py:628-644): cells must already be set in d_H;
+ * grows all chains of n walkers by random insertion (retry until no overlap, at most
+ * max_attempts per chain).  d_status[k] = attempts used, or -1 if a chain did not fit. */
+int hans_grow(const hans_cfg *cfg, const double *d_H, double *d_R, int n, uint64_t seed,
+              uint32_t gid_base, int max_attempts, int32_t *d_status, void *stream);
+/* one attempt for one chain of one walker: alk.alkane_grow_chain(ichain, ibox, 1) (MCNS.py:642);
+ * d_status[0] = 1 if the chain was placed, -1 if it overlapped (ifail). */
+int hans_grow_chain(const hans_cfg *cfg, const double *d_H, double *d_R, int walker, int ichain,
+                    uint64_t seed, uint32_t gid, uint32_t attempt, int32_t *d_status, void *stream);
+
+/* ---- nested-sampling iteration helpers (mpihans.py:210-245) -----------------------------------
+ * Local MAXLOC over d_vol[0..n) (mpihans.py:211-212): writes d_out = {max volume, (double)index};
+ * ties resolve to the lowest index, as list.index does. */
+int hans_argmax(const double *d_vol, int n, double *d_out2, void *stream);
+
+/* Clone (mpihans.py:226-237, MCNS.py:550-580): copy cell + beads (+ volume) of walker src of the
+ * source pool over walker dst of the destination pool.  The source may be a staging buffer
+ * received from another GPU (then src = 0).  d_dst_index/d_src_index are optional DEVICE scalars
+ * (int32) that override dst/src, so the copy can be enqueued before the host knows the argmax.
+ * If d_enable is non-NULL the copy happens only when *d_enable != 0. */
+int hans_clone(const hans_cfg *cfg, const double *d_srcH, const double *d_srcR,
+               const double *d_srcvol, int src, const int32_t *d_src_index, double *d_dstH,
+               double *d_dstR, double *d_dstvol, int dst, const int32_t *d_dst_index,
+               const int32_t *d_enable, void *stream);
+
+/* FP32 FFMA issue-rate probe used as the roofline denominator in bench.py: runs `iters`
+ * dependent-chain-free FFMAs per thread on the whole chip, returns achieved TFLOP/s. */
+int hans_ffma_peak(int iters, double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANS_B200_H */

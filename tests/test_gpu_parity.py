@@ -1,0 +1,258 @@
+"""GPU <-> CPU-oracle parity through the C ABI (libhans_b200.so).
+
+Bar: BIT-EXACT.  Accept/reject decisions, reasons, boltz factors and the float64 post-move state
+(cell + every bead) must be identical to the oracle's on the same proposals and configurations
+(BASELINE.json north_star, correctness level 1).
+"""
+import numpy as np
+import pytest
+
+from common import SHAPES, compress, make_walkers
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hans_b200 import engine
+    return engine
+
+
+def make_pool(eng, shape, H, R, kw, seed=0, tpw=0):
+    nchains, nbeads, mr = SHAPES[shape]
+    pool = eng.WalkerPool(H.shape[0], nchains, nbeads, mr, seed=seed, threads_per_walker=tpw, **kw)
+    pool.set_state(H, R)
+    return pool
+
+
+def assert_state_equal(pool, H, R):
+    gH, gR = pool.get_state()
+    assert np.array_equal(gH.view(np.uint64), H.view(np.uint64)), "cell differs from oracle"
+    bad = np.nonzero((gR.view(np.uint64) != R.view(np.uint64)).any(axis=(1, 2)))[0]
+    assert bad.size == 0, f"bead coordinates differ from oracle for walkers {bad[:8]}"
+
+
+# ---- a11: overlap predicate --------------------------------------------------------------------
+@pytest.mark.parametrize("shape", ["C1", "C2", "C4s", "dimer"])
+@pytest.mark.parametrize("tpw", [32, 64, 128, 256])
+def test_overlap_predicate(eng, oracle, shape, tpw):
+    cfg, H, R, kw = make_walkers(shape, 24, seed=11)
+    rng = np.random.default_rng(5)
+    # adversarial variants: random displacement of one bead so that roughly half the walkers overlap,
+    # wrapped copies (bead moved by a lattice vector), sheared cells
+    for w in range(H.shape[0]):
+        if w % 3 == 0:
+            i, j = rng.choice(R.shape[1], 2, replace=False)
+            d = rng.normal(size=3)
+            R[w, i] = R[w, j] + d / np.linalg.norm(d) * rng.uniform(0.9, 1.1)
+        if w % 4 == 1:
+            i = rng.integers(R.shape[1])
+            R[w, i] += rng.integers(-2, 3, size=3) @ H[w]
+        if w % 5 == 2:
+            H[w, 0] += 0.3 * H[w, 1]
+    pool = make_pool(eng, shape, H, R, kw, tpw=tpw)
+    for inter_only in (False, True):
+        got = pool.check_overlap(inter_only=inter_only).cpu().numpy()
+        want = np.array([oracle.check_overlap(cfg, H[w], R[w], inter_only) for w in range(H.shape[0])])
+        assert np.array_equal(got, want)
+        assert 0 < want.sum() < len(want)
+    # subset through ids
+    ids = [5, 0, 17]
+    got = pool.check_overlap(ids=ids).cpu().numpy()
+    assert np.array_equal(got, [oracle.check_overlap(cfg, H[w], R[w]) for w in ids])
+
+
+def test_overlap_near_contact(eng, oracle):
+    """Pairs placed within a few ulp of r = sigma: strict r^2 < 1 must agree bit for bit."""
+    nchains, nbeads, mr = 2, 1, [1, 6, 0, 0, 3, 3]
+    cfg = oracle.make_cfg(nchains, nbeads, mr)
+    n = 256
+    H = np.tile(np.diag([5.0, 6.0, 7.0]), (n, 1, 1))
+    H[:, 1, 0] = 0.7
+    R = np.zeros((n, 2, 3))
+    rng = np.random.default_rng(3)
+    for w in range(n):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        R[w, 0] = rng.uniform(-3, 3, size=3)
+        R[w, 1] = R[w, 0] + d * (1.0 + (w - n // 2) * 2.0 ** -52) + rng.integers(-1, 2, size=3) @ H[w]
+    from hans_b200 import engine
+    pool = engine.WalkerPool(n, nchains, nbeads, mr)
+    pool.set_state(H, R)
+    got = pool.check_overlap().cpu().numpy()
+    want = np.array([oracle.check_overlap(cfg, H[w], R[w]) for w in range(n)])
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < n
+
+
+# ---- a12/a13/a16: cell metrics ------------------------------------------------------------------
+def test_cell_metrics(eng, oracle):
+    rng = np.random.default_rng(1)
+    n = 64
+    H = np.tile(np.eye(3) * 7.0, (n, 1, 1)) + rng.normal(scale=1.5, size=(n, 3, 3))
+    from hans_b200 import engine
+    pool = engine.WalkerPool(n, 4, 2, [1, 1, 1, 0, 1, 1])
+    pool.H.copy_(torch.as_tensor(H))
+    v, a, c = (t.cpu().numpy() for t in pool.cell_metrics())
+    for w in range(n):
+        assert v[w] == oracle.volume(H[w])
+        assert a[w] == oracle.min_aspect_ratio(H[w])
+        assert c[w] == oracle.max_abs_cos(H[w])
+
+
+# ---- a4..a10, a14, a15: every move type in replay mode --------------------------------------------
+def _replay_case(eng, oracle, shape, tpw, nwalkers=12, nmoves=400, seed=21, dense=False, mode=0, **kw):
+    cfg, H, R, k = make_walkers(shape, nwalkers, seed=seed, **kw)
+    if dense:
+        H, R = compress(cfg, H, R, dense, seed)
+    props = np.stack([oracle.gen_proposals(cfg, 99, w, 0, nmoves) for w in range(nwalkers)])
+    limit = float(np.max([oracle.volume(H[w]) for w in range(nwalkers)]))
+    pool = make_pool(eng, shape, H, R, k, tpw=tpw)
+    got = pool.replay(None, props, volume_limit=limit, mode=mode)
+    want = np.stack([oracle.replay(cfg, H[w], R[w], props[w], limit, mode) for w in range(nwalkers)])
+    for f in ("accepted", "reason"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["boltz"].view(np.uint64), want["boltz"].view(np.uint64))
+    assert_state_equal(pool, H, R)
+    return props, want
+
+
+@pytest.mark.parametrize("shape,tpw", [("C1", 32), ("C1", 128), ("C2", 32), ("C2", 64), ("C4s", 32), ("C4s", 256),
+                                        ("dimer", 32)])
+def test_replay_all_moves(eng, oracle, shape, tpw):
+    # equal weights so that every move type (incl. dihedral where nbeads >= 4) is exercised
+    nchains, nbeads, _ = SHAPES[shape]
+    SHAPES["_tmp"] = (nchains, nbeads, [1, 1, 1, 1 if nbeads >= 4 else 0, 1, 1])
+    try:
+        props, dec = _replay_case(eng, oracle, "_tmp", tpw)
+    finally:
+        del SHAPES["_tmp"]
+    types = set(np.unique(props["type"]))
+    assert types >= ({0, 1, 2, 4, 5} if nbeads > 1 else {0, 1, 4, 5})
+    # both outcomes seen
+    assert 0 < dec["accepted"].mean() < 1
+
+
+def test_replay_dense_rejections(eng, oracle):
+    """Dense regime: most moves are rejected by overlap, early exit paths are hit."""
+    props, dec = _replay_case(eng, oracle, "C2", 32, nwalkers=8, nmoves=600, dense=0.7, dr_max=0.6, dv_max=3.0)
+    assert (dec["reason"] == 1).mean() > 0.2
+
+
+def test_replay_propose_mode(eng, oracle):
+    """hs_alkane entry-point semantics: trial state left in place, boltz returned."""
+    _replay_case(eng, oracle, "C1", 32, nwalkers=6, nmoves=60, mode=1)
+
+
+def test_replay_invalid_and_edge(eng, oracle):
+    """dihedral on short chains, dV driving the volume negative, u_acc = 0, ids subset."""
+    cfg, H, R, k = make_walkers("dimer", 4, seed=2)
+    props = np.zeros((4, 4), dtype=oracle.PROPOSAL_DTYPE)
+    props["type"][:, 0] = 3; props["idx0"][:, 0] = 3          # dihedral impossible on dimers
+    props["type"][:, 1] = 0; props["p"][:, 1, 0] = -1e9        # V + dV <= 0
+    props["type"][:, 2] = 0; props["p"][:, 2, 0] = -1.0; props["u_acc"][:, 2] = 0.0
+    props["type"][:, 3] = 1; props["p"][:, 3, :3] = [100.0, -250.0, 1e-9]; props["ichain"][:, 3] = 31
+    pool = make_pool(eng, "dimer", H, R, k)
+    got = pool.replay([2, 0], props[:2], volume_limit=1e300)
+    want = np.stack([oracle.replay(cfg, H[w], R[w], props[0], 1e300) for w in (2, 0)])
+    assert np.array_equal(got["accepted"], want["accepted"]) and np.array_equal(got["reason"], want["reason"])
+    assert list(want["reason"][0][:2]) == [6, 6]
+    assert_state_equal(pool, H, R)
+
+
+# ---- a1: the fused MC_run, self-driving from Philox ------------------------------------------------
+@pytest.mark.parametrize("shape,tpw,sweeps", [("C1", 32, 6), ("C1", 64, 3), ("C2", 32, 10), ("C2", 128, 4),
+                                               ("C4s", 32, 3), ("C4s", 256, 2), ("dimer", 32, 5)])
+def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
+    nw = 10
+    cfg, H, R, k = make_walkers(shape, nw, seed=31)
+    seed = 424242
+    limit = float(np.median([oracle.volume(H[w]) for w in range(nw)]))  # ceiling bites for half
+    pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=tpw)
+    pool.gid_base = 1000
+    ids = [7, 2, 9, 0, 4]
+    att, acc = pool.mc_run(sweeps, ids=ids, volume_limit=limit)
+    att2, acc2 = pool.mc_run(1, ids=ids, volume_limit=limit)  # continues the per-walker counters
+    ctrs = np.zeros(nw, dtype=np.uint64)
+    o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, ids, sweeps, limit, seed, 1000 + np.array(ids), ctrs)
+    o_vol, o_att2, o_acc2 = oracle.mc_run_many(cfg, H, R, ids, 1, limit, seed, 1000 + np.array(ids), ctrs)
+    assert np.array_equal(att.cpu().numpy().astype(np.uint64), o_att)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+    assert np.array_equal(acc2.cpu().numpy().astype(np.uint64), o_acc2)
+    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+    assert_state_equal(pool, H, R)
+    assert np.array_equal(pool.vol.cpu().numpy()[ids], o_vol)
+    nmoves = (sweeps + 1) * oracle.moves_per_sweep(cfg.nbeads, cfg.nchains)
+    assert int(att.sum() + att2.sum()) == nmoves * len(ids)
+    assert int(pool.pair_tests.item()) > 0
+    assert not pool.check_overlap().cpu().numpy().any()
+
+
+def test_mc_run_device_limit_and_no_counters(eng, oracle):
+    cfg, H, R, k = make_walkers("C1", 4, seed=8)
+    pool = make_pool(eng, "C1", H, R, k, seed=5)
+    lim = torch.tensor([1400.0], dtype=torch.float64, device=pool.device)
+    a, b = pool.mc_run(2, d_volume_limit=lim, counters=False)
+    assert a is None and b is None
+    ctrs = np.zeros(4, dtype=np.uint64)
+    oracle.mc_run_many(cfg, H, R, np.arange(4), 2, 1400.0, 5, np.arange(4), ctrs)
+    assert_state_equal(pool, H, R)
+
+
+# ---- a21: initial configurations -----------------------------------------------------------------
+@pytest.mark.parametrize("shape", ["C1", "C2", "C4s"])
+def test_grow_matches_oracle(eng, oracle, shape):
+    nchains, nbeads, mr = SHAPES[shape]
+    nw = 6
+    pool = eng.WalkerPool(nw, nchains, nbeads, mr, seed=77, gid_base=3)
+    pool.set_initial_cells()
+    st = pool.grow()
+    cfg = oracle.make_cfg(nchains, nbeads, mr)
+    H, R = oracle.grow_walkers(cfg, nw, seed=77, gid0=3)
+    assert_state_equal(pool, H, R)
+    assert (st >= nchains).all()
+    assert not pool.check_overlap().cpu().numpy().any()
+    v = pool.vol.cpu().numpy()
+    assert np.allclose(v, 0.999 ** 3 * 15 * nchains * nbeads)
+
+
+# ---- a17/a18: NS iteration helpers ---------------------------------------------------------------
+def test_argmax_and_clone(eng, oracle):
+    cfg, H, R, k = make_walkers("C2", 40, seed=4)
+    pool = make_pool(eng, "C2", H, R, k)
+    vols = pool.vol.cpu().numpy().copy()
+    # introduce a tie: the lowest index must win (list.index semantics, mpihans.py:212)
+    H[33] = H[int(np.argmax(vols))]
+    H[12] = H[33]
+    pool.set_state(H, R)
+    vols = pool.vol.cpu().numpy()
+    out = pool.argmax().cpu().numpy()
+    assert out[0] == vols.max() and int(out[1]) == int(np.argmax(vols))
+    pool.clone(src=3, dst=int(out[1]))
+    gH, gR = pool.get_state()
+    assert np.array_equal(gH[int(out[1])], H[3]) and np.array_equal(gR[int(out[1])], R[3])
+    assert pool.vol.cpu().numpy()[int(out[1])] == vols[3]
+    # device-side indices + enable flag
+    d_src = torch.tensor([5], dtype=torch.int32, device=pool.device)
+    d_dst = torch.tensor([6], dtype=torch.int32, device=pool.device)
+    off = torch.tensor([0], dtype=torch.int32, device=pool.device)
+    pool.clone(0, 0, d_src=d_src, d_dst=d_dst, d_enable=off)
+    assert np.array_equal(pool.get_state()[1][6], R[6])
+    pool.clone(0, 0, d_src=d_src, d_dst=d_dst)
+    assert np.array_equal(pool.get_state()[1][6], R[5])
+
+
+def test_change_box(eng, oracle):
+    cfg, H, R, k = make_walkers("C1", 5, seed=6)
+    pool = make_pool(eng, "C1", H, R, k)
+    rng = np.random.default_rng(0)
+    dH = rng.normal(scale=0.2, size=(3, 3, 3))
+    ids = [4, 1, 2]
+    pool.change_box(ids, dH)
+    for n, w in enumerate(ids):
+        oracle.change_box(cfg, H[w], R[w], dH[n])
+    assert_state_equal(pool, H, R)
