@@ -61,7 +61,7 @@ __device__ __forceinline__ double det3(const double *H)
     return (H[0] * c00 + H[1] * c01) + H[2] * c02;
 }
 
-__device__ __forceinline__ void hinv(const double *H, double *Hi)
+__device__ __noinline__ void hinv(const double *H, double *Hi)
 {
     const double c00 = H[4] * H[8] - H[5] * H[7];
     const double c01 = H[5] * H[6] - H[3] * H[8];
@@ -100,7 +100,7 @@ __device__ __forceinline__ void cross3(const double *a, const double *b, double 
 }
 
 // alk.box_min_aspect_ratio / min_aspect_ratio (MCNS.py:97-118)
-__device__ inline double min_aspect_ratio(const double *H)
+__device__ __noinline__ double min_aspect_ratio(const double *H)
 {
     const double vol = fabs(det3(H));
     double best = 1.7976931348623157e308;
@@ -117,7 +117,7 @@ __device__ inline double min_aspect_ratio(const double *H)
 }
 
 // largest |cos| between two cell vectors; min_angle (MCNS.py:120-133) = arccos of it
-__device__ inline double max_abs_cos(const double *H)
+__device__ __noinline__ double max_abs_cos(const double *H)
 {
     double best = 0.0;
 #pragma unroll
@@ -177,7 +177,7 @@ struct Prop {
     double u_acc;
 };
 
-__device__ inline Prop gen_proposal(const hans_cfg &c, uint64_t seed, uint32_t gid, uint64_t ctr)
+__device__ __noinline__ Prop gen_proposal(const hans_cfg &c, uint64_t seed, uint32_t gid, uint64_t ctr)
 {
     const int wl = threadIdx.x & 31;
     double ua, ub;

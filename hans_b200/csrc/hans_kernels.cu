@@ -94,48 +94,47 @@ __device__ bool chain_intra_overlap(WCtx &w, int b0, const double *H, const doub
 }
 
 // all inter-chain pairs (and optionally the intra-chain ones) of the beads in (X,Y,Z).
-// Chain pairs are enumerated round-robin: (ci, (ci+d) mod nc), d = 1..(nc-1)/2, plus the
-// antipodal pairs when nc is even; bead pairs inside a chain pair are nb*nb.
+// Bead-level round robin: lane owns bead i (registers) and walks the offsets d = 1..N/2 with
+// j = (i + d) mod N, so a warp reads consecutive shared-memory words (no bank conflicts, no index
+// division) and every unordered pair is visited exactly once (for even N the antipodal offset
+// d = N/2 is taken by the lower half only).  Same-chain pairs are skipped unless with_intra and
+// their separation along the chain exceeds nexclude.
 template <int T>
 __device__ bool all_overlap(WCtx &w, const double *X, const double *Y, const double *Z, const double *H,
                             const double *Hi, bool with_intra)
 {
-    const int nb = w.nb, nc = w.nc, nb2 = nb * nb;
-    const int full = nc * ((nc - 1) / 2);
-    const int ncp = nc * (nc - 1) / 2;
-    const int P = ncp * nb2;
+    const int nb = w.nb, N = w.N, half = N >> 1;
+    const bool even = (N & 1) == 0;
+    // rows per pass and offset groups: when the group has more lanes than beads, split the offsets
+    const int RB = T < N ? T : N;
+    const int DG = T < N ? 1 : T / N;
+    const int li = w.lane % RB, dg = w.lane / RB;
+    const bool lane_on = dg < DG;
     bool ov = false;
-    constexpr int U = 4; // pair tests per lane between votes
-    for (int base = 0; base < P; base += T * U) {
+    constexpr int U = 4; // offsets per lane between votes
+    for (int i0 = 0; i0 < N; i0 += RB) {
+        const int i = i0 + li;
+        const bool row_on = lane_on && i < N;
+        const int ii = row_on ? i : 0;
+        const double xi = X[ii], yi = Y[ii], zi = Z[ii];
+        const int c0 = (ii / nb) * nb, c1 = c0 + nb;
+        for (int d0 = 1; d0 <= half; d0 += DG * U) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = base + u * T + w.lane;
-            if (p < P) {
-                const int cp = p / nb2, r = p - cp * nb2;
-                int ci, cj;
-                if (cp < full) { const int d = cp / nc; ci = cp - d * nc; cj = ci + d + 1; if (cj >= nc) cj -= nc; }
-                else { ci = cp - full; cj = ci + nc / 2; }
-                const int bi = r / nb, bj = r - bi * nb;
-                const int i = ci * nb + bi, j = cj * nb + bj;
-                ov |= (pair_r2(H, Hi, X[j] - X[i], Y[j] - Y[i], Z[j] - Z[i]) < 1.0);
-                w.pairs += 1;
+            for (int u = 0; u < U; ++u) {
+                const int d = d0 + u * DG + dg;
+                if (row_on && d <= half && !(even && d == half && i >= half)) {
+                    int j = i + d;
+                    if (j >= N) j -= N;
+                    const bool same = (j >= c0) && (j < c1);
+                    const int sep = j > i ? j - i : i - j;
+                    if (!same || (with_intra && sep > w.nex)) {
+                        ov |= (pair_r2(H, Hi, X[j] - xi, Y[j] - yi, Z[j] - zi) < 1.0);
+                        w.pairs += 1;
+                    }
+                }
             }
+            if (gany<T>(ov)) return true;
         }
-        if (gany<T>(ov)) return true;
-    }
-    if (with_intra && w.npc > 0) {
-        const int Q = nc * w.npc;
-        for (int base = 0; base < Q; base += T) {
-            const int q = base + w.lane;
-            if (q < Q) {
-                const int ch = q / w.npc;
-                const uchar2 jb = w.itab[q - ch * w.npc];
-                const int i = ch * nb + jb.x, j = ch * nb + jb.y;
-                ov |= (pair_r2(H, Hi, X[j] - X[i], Y[j] - Y[i], Z[j] - Z[i]) < 1.0);
-                w.pairs += 1;
-            }
-        }
-        if (gany<T>(ov)) return true;
     }
     return false;
 }

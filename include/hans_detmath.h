@@ -26,8 +26,12 @@
 
 #if defined(__CUDACC__)
 #define HANS_HD __host__ __device__ __forceinline__
+/* the transcendental-sized routines are kept out of line on the GPU: one copy in the instruction
+ * cache instead of one per call site (they are off the pair-test hot loop) */
+#define HANS_HD_BIG __host__ __device__ __noinline__
 #else
 #define HANS_HD static inline
+#define HANS_HD_BIG static inline
 #endif
 
 #define HD_PI 3.14159265358979323846264338327950288
@@ -80,7 +84,7 @@ HANS_HD double hd_pow2i(int k)
 }
 
 /* exp(x).  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, Taylor to r^13. */
-HANS_HD double hd_exp(double x)
+HANS_HD_BIG double hd_exp(double x)
 {
     if (x != x) return x;
     if (x > 709.0) return hd_from_bits(0x7ff0000000000000ull);
@@ -112,7 +116,7 @@ HANS_HD double hd_exp(double x)
 }
 
 /* log(x) for finite x > 0 (normal numbers; subnormals are scaled up first). */
-HANS_HD double hd_log(double x)
+HANS_HD_BIG double hd_log(double x)
 {
     if (x != x) return x;
     if (x <= 0.0) return (x == 0.0) ? -hd_from_bits(0x7ff0000000000000ull)
@@ -148,7 +152,7 @@ HANS_HD double hd_log(double x)
 }
 
 /* sin and cos of x, intended for |x| <= ~1e5 (the engine clamps rotation amplitudes to pi). */
-HANS_HD void hd_sincos(double x, double *sn, double *cs)
+HANS_HD_BIG void hd_sincos(double x, double *sn, double *cs)
 {
     const double two_over_pi = 6.36619772367581382433e-01;
     const double pio2_1 = 1.57079632673412561417e+00;  /* first 33 bits of pi/2 */
@@ -191,7 +195,7 @@ HANS_HD void hd_sincos(double x, double *sn, double *cs)
 }
 
 /* cbrt(x) for x > 0: exp(log(x)/3) polished by two Newton steps. */
-HANS_HD double hd_cbrt(double x)
+HANS_HD_BIG double hd_cbrt(double x)
 {
     if (!(x > 0.0)) return (x == 0.0) ? 0.0 : -hd_from_bits(0x7ff8000000000000ull);
     double y = hd_exp(hd_log(x) / 3.0);
