@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the nested-sampling MC walker hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port on host cores)
+
+A "step" is one nested-sampling iteration (mpihans.py:210-245) over the resident walkers:
+local/global MAXLOC, clone, and `walklength` sweeps of MC moves for every active walker.
+Workload (BASELINE.json configs[1], "C2"): single hard spheres nbeads=1 nchains=64, 1024 walkers
+per GPU, walklength=40, default move ratio 1,192,0,0,3,3; every resident walker walks each
+iteration (1024 virtual ranks of nwalkers=1).  Weak scaling: walkers per GPU fixed.
+Metric: MC move attempts/s (whole job); NS iterations/s is reported beside it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nchains, nbeads, move_ratio, walkers per GPU, mean algorithmic pair tests per move)
+    "C2": (64, 1, [1, 192, 0, 0, 3, 3], 1024, 132.0),
+    "C3": (16, 6, [3, 48, 32, 0, 3, 3], 1024, 922.0),
+    "C4": (32, 12, [3, 32, 32, 16, 3, 3], 512, 11235.0),
+}
+FLOP_PER_PAIR = 45.0
+WALKLENGTH = 40
+SEED = 20261019
+
+
+def algorithmic_pairs_per_move(nchains, nbeads, move_ratio):
+    """No-early-exit inter-chain pair tests per move, weighted by the move ratio."""
+    N = nchains * nbeads
+    single = nbeads * (N - nbeads)
+    box = (N * N - nchains * nbeads * nbeads) / 2.0
+    mr = np.asarray(move_ratio, dtype=float)
+    w = mr / mr.sum()
+    return float(w[1] * single + w[2] * single + w[3] * single + (w[0] + w[4] + w[5]) * box)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/) on the host cores.  TEST INFRASTRUCTURE used as the baseline.
+# ---------------------------------------------------------------------------------------------------
+def cpu_prepare(name, nwalk, initial_walk=20):
+    from oracle import oracle as ho
+    nchains, nbeads, mr, _, _ = WORKLOADS[name]
+    cfg = ho.make_cfg(nchains, nbeads, mr)
+    H, R = ho.grow_walkers(cfg, nwalk, SEED)
+    ctrs = np.zeros(nwalk, dtype=np.uint64)
+    ho.mc_run_many(cfg, H, R, np.arange(nwalk), initial_walk, 1e300, SEED, np.arange(nwalk), ctrs)
+    return ho, cfg, H, R, ctrs
+
+
+def cpu_native_rate(name, seconds=12.0, threads=None):
+    """Variant (ii) of BASELINE.md: the oracle's native MC_run loop, one walker per OpenMP thread."""
+    threads = threads or os.cpu_count()
+    nwalk = max(threads * 2, 8)
+    ho, cfg, H, R, ctrs = cpu_prepare(name, nwalk)
+    mps = ho.moves_per_sweep(cfg.nbeads, cfg.nchains)
+    vols = np.array([ho.volume(H[w]) for w in range(nwalk)])
+    limit = float(vols.max())
+    moves, t0 = 0, time.perf_counter()
+    while True:
+        ho.mc_run_many(cfg, H, R, np.arange(nwalk), WALKLENGTH, limit, SEED, np.arange(nwalk), ctrs, nthreads=threads)
+        moves += nwalk * WALKLENGTH * mps
+        dt = time.perf_counter() - t0
+        if dt > seconds:
+            break
+    return moves / dt, threads, f"{nwalk} walkers x {WALKLENGTH} sweeps repeated for {dt:.1f} s on {threads} OpenMP threads"
+
+
+def _shaped_worker(args):
+    """Variant (i): a Python loop shaped like MC_run (MCNS.py:304-383): per move one proposal call
+    and one apply call through ctypes, i.e. the reference's interpreter-bound structure."""
+    name, wid, seconds = args
+    import ctypes as C
+    ho, cfg, H, R, ctrs = cpu_prepare(name, 1)
+    L = ho.lib()
+    prop = np.zeros(1, dtype=ho.PROPOSAL_DTYPE)
+    dec = np.zeros(1, dtype=ho.DECISION_DTYPE)
+    mps = ho.moves_per_sweep(cfg.nbeads, cfg.nchains)
+    limit = ho.volume(H[0])
+    accepted = np.zeros(6)
+    attempted = np.zeros(6)
+    m, t0 = 0, time.perf_counter()
+    Hp, Rp, pp, dp = H[0].ctypes.data, R[0].ctypes.data, prop.ctypes.data, dec.ctypes.data
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(mps):
+            L.ho_gen_proposal(C.byref(cfg), SEED, wid, m, pp)
+            L.ho_apply_proposal(C.byref(cfg), Hp, Rp, pp, C.c_double(limit), 0, dp)
+            t = int(prop["type"][0])
+            attempted[t] += 1
+            accepted[t] += dec["accepted"][0]
+            m += 1
+    return m / (time.perf_counter() - t0)
+
+
+def cpu_shaped_rate(name, seconds=8.0, procs=None):
+    import multiprocessing as mp
+    procs = procs or os.cpu_count()
+    # spawn, not fork: the parent has live OpenMP / CUDA state that must not be inherited
+    with mp.get_context("spawn").Pool(procs) as pool:
+        rates = pool.map(_shaped_worker, [(name, w, seconds) for w in range(procs)])
+    return float(np.sum(rates)), procs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    nchains, nbeads, mr, nw, _ = WORKLOADS[name]
+    threads = os.cpu_count()
+    nwalk = max(threads * 2, 8)
+    ho, cfg, H, R, ctrs = cpu_prepare(name, nwalk)
+    mps = ho.moves_per_sweep(nbeads, nchains)
+    limit = float(max(ho.volume(H[w]) for w in range(nwalk)))
+    ids = np.arange(nwalk)
+
+    def step():
+        ho.mc_run_many(cfg, H, R, ids, WALKLENGTH, limit, SEED, ids, ctrs, nthreads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    moves = args.steps * nwalk * WALKLENGTH * mps
+    value = moves / dt
+    sample = f"each step = {nwalk} walkers x {WALKLENGTH} sweeps ({nwalk * WALKLENGTH * mps} moves) of the {name} shape"
+    line = {
+        "impl": "reference", "metric": "mc_move_attempts_per_s", "value": value, "unit": "moves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: nbeads={nbeads} nchains={nchains} walklength={WALKLENGTH} move_ratio={mr}",
+                   "note": "oracle stand-in for hs_alkane via mpihans.py/MPI -- real hs_alkane unavailable in this image"},
+        "cpu_baseline": {"value": value, "unit": "moves/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ns_iterations_per_s": None, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    from hans_b200 import engine
+    from hans_b200.ns import NestedSampler
+
+    name = args.workload
+    nchains, nbeads, mr, nw_default, _ = WORKLOADS[name]
+    nw = args.walkers or nw_default
+    N = nchains * nbeads
+    pool = engine.WalkerPool(nw, nchains, nbeads, mr, device=dev, seed=SEED, gid_base=rank * nw,
+                             threads_per_walker=args.tpw)
+    pool.set_initial_cells()
+    pool.grow()
+    pool.mc_run(args.initial_walk, counters=False)  # perturb_initial_configs, MCNS.py:527-546
+    ns = NestedSampler(pool, nwalkers=1, walklength=WALKLENGTH, rank=rank, world=world, group=group, seed=SEED,
+                       traj_interval=0, log_cap=max(4096, args.steps + args.warmup + 8))
+    ns.walk_counters = False
+    mps = pool.moves_per_sweep
+    moves_per_step = world * nw * WALKLENGTH * mps
+    apm = algorithmic_pairs_per_move(nchains, nbeads, mr)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=group)
+            torch.cuda.synchronize(dev)
+
+    def timed_region(steps, h2d=False, kernel_events=None):
+        """K iterations on the device clock; returns ms (this rank)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for s in range(steps):
+            if h2d:
+                pool.H.copy_(hH, non_blocking=True)   # step inputs from pinned host memory
+                pool.R.copy_(hR, non_blocking=True)
+                pool.refresh_volumes()
+            if kernel_events is not None:
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ns.step_with_events(k0, k1)
+                kernel_events.append((k0, k1))
+            else:
+                ns.step()
+            if h2d:
+                hvol.copy_(pool.vol, non_blocking=True)  # step result: the walker volumes
+                hlim.copy_(ns.d_limit, non_blocking=True)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item())
+
+    # FP32 FFMA issue peak of this GPU (roofline denominator; MEASURED_PEAKS.json has no FP32 figure)
+    ffma_peak = engine.ffma_peak_tflops()
+
+    # ---- device-resident timing (value) --------------------------------------------------------
+    ns.run(args.warmup)
+    launches0 = pool.launches
+    pool.pair_tests.zero_()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    kev = []
+    ms = max_over_ranks(timed_region(args.steps, kernel_events=kev))
+    clk = clocks.stop() if rank == 0 else {}
+    launches = pool.launches - launches0
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    executed_pairs = int(pool.pair_tests.item()) / max(args.steps, 1)
+    value = args.steps * moves_per_step / (ms * 1e-3)
+    log, _ = ns.flush()
+    vol_first, vol_last = float(log[0, 1]), float(log[-1, 1])
+
+    # ---- end-to-end through the public API with host buffers (e2e) -----------------------------
+    hH = torch.empty(pool.H.shape, dtype=torch.float64).pin_memory()
+    hR = torch.empty(pool.R.shape, dtype=torch.float64).pin_memory()
+    hvol = torch.empty(pool.vol.shape, dtype=torch.float64).pin_memory()
+    hlim = torch.empty(1, dtype=torch.float64).pin_memory()
+    hH.copy_(pool.H); hR.copy_(pool.R)
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(args.steps // 2, 1)
+    timed_region(min(args.warmup, 3), h2d=True)
+    ms_e2e = max_over_ranks(timed_region(e2e_steps, h2d=True))
+    e2e_value = e2e_steps * moves_per_step / (ms_e2e * 1e-3)
+    h2d_bytes = hH.numel() * 8 + hR.numel() * 8
+    d2h_bytes = hvol.numel() * 8 + 8
+    ns.flush()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            rate, threads, sample = cpu_native_rate(name, seconds=args.cpu_seconds)
+            cpu = {"value": rate, "unit": "moves/s", "cores": threads, "kind": "port", "sample": sample}
+            if args.cpu_shaped:
+                srate, procs = cpu_shaped_rate(name, seconds=min(args.cpu_seconds, 8.0))
+                cpu["reference_shaped"] = {"value": srate, "unit": "moves/s", "cores": procs,
+                                           "sample": "per-move Python loop over the oracle's C entry points "
+                                                     "(MC_run-shaped, BASELINE.md variant i), one process per core"}
+        except Exception as e:  # the baseline must never take the GPU line down
+            cpu = {"value": None, "unit": "moves/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        pairs_per_launch = apm * nw * WALKLENGTH * mps
+        achieved = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
+        achieved_exec = FLOP_PER_PAIR * (executed_pairs / world) / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": "mc_move_attempts_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: nbeads={nbeads} nchains={nchains} walkers_per_gpu={nw} walklength={WALKLENGTH} "
+                                   f"move_ratio={mr}", "total_walkers": nw * world, "moves_per_iteration": moves_per_step,
+                       "initial_walk_sweeps": args.initial_walk, "parallel_mode": "every resident walker walks each iteration",
+                       "threads_per_walker": args.tpw or "default", "volume_first_last": [vol_first, vol_last],
+                       "cache": "working set (walker state) lives in shared memory for the whole walk; "
+                                "HBM traffic is one read+write of the state per launch; no L2 flush needed"},
+            "ns_iterations_per_s": args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / ffma_peak, "traffic": None,
+                         "kernel": "hb::walk_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "kernel_share_of_step": kernel_ms / (ms / args.steps),
+                         "algorithmic_pair_tests_per_launch": pairs_per_launch, "flop_per_pair_test": FLOP_PER_PAIR,
+                         "executed_pair_tests_per_launch": executed_pairs / world, "achieved_executed": achieved_exec,
+                         "peak_source": "FFMA issue-rate probe (hans_ffma_peak) run in this process; "
+                                        "MEASURED_PEAKS.json holds no FP32 figure"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(group=group)
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: the workload's)")
+    ap.add_argument("--initial-walk", type=int, default=100, help="unconstrained sweeps after growth (reference: 1000)")
+    ap.add_argument("--tpw", type=int, default=0, help="threads per walker (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-shaped", action="store_true", help="also time the MC_run-shaped Python loop (BASELINE.md variant i)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

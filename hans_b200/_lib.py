@@ -43,11 +43,23 @@ PROPOSAL_DTYPE = np.dtype([
 DECISION_DTYPE = np.dtype([("accepted", "<i4"), ("reason", "<i4"), ("boltz", "<f8")], align=True)
 assert PROPOSAL_DTYPE.itemsize == 64 and DECISION_DTYPE.itemsize == 16
 
+class NsArgs(C.Structure):
+    """struct hans_ns_args (include/hans_b200.h)."""
+    _fields_ = [
+        ("N", C.c_int32), ("nlocal", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("nw_per_vrank", C.c_int32), ("traj_interval", C.c_int32), ("traj_slots", C.c_int32), ("log_cap", C.c_int32),
+        ("seed", C.c_uint64),
+        ("d_H", C.c_void_p), ("d_R", C.c_void_p), ("d_vol", C.c_void_p),
+        ("d_iter", C.c_void_p), ("d_rec", C.c_void_p), ("d_gathered", C.c_void_p), ("d_limit", C.c_void_p),
+        ("d_log", C.c_void_p), ("d_ids", C.c_void_p), ("d_traj", C.c_void_p), ("d_traj_iter", C.c_void_p),
+    ]
+
+
 EXPORTS = [
     "hans_abi_version", "hans_last_error", "hans_device_count", "hans_walker_smem_bytes",
     "hans_moves_per_sweep", "hans_default_threads_per_walker", "hans_mc_run_batch", "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
-    "hans_argmax", "hans_clone", "hans_ffma_peak",
+    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ffma_peak",
 ]
 
 
@@ -99,6 +111,8 @@ def _load():
     L.hans_grow_chain.argtypes = [cp, vp, vp, i32, i32, u64, u32, u32, vp, vp]
     L.hans_argmax.argtypes = [vp, i32, vp, vp]
     L.hans_clone.argtypes = [cp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
+    L.hans_ns_pack.argtypes = [C.POINTER(NsArgs), vp]
+    L.hans_ns_resolve.argtypes = [C.POINTER(NsArgs), vp]
     L.hans_ffma_peak.argtypes = [i32, C.POINTER(f64), vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -721,6 +721,126 @@ __global__ void clone_kernel(int N, const double *sH, const double *sR, const do
     if (threadIdx.x == 0 && dvol && svol) dvol[d] = svol[s];
 }
 
+// ---------------------------------------------------------------------------------------------
+// nested-sampling iteration helpers (mpihans.py:210-245), single CTA each
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t STREAM_NS = 2u;
+
+__device__ __forceinline__ unsigned long long ns_draw(unsigned long long seed, long long it, uint32_t c2, uint32_t blk)
+{
+    uint32_t x[4];
+    philox4x32_10((uint32_t)it, (uint32_t)((unsigned long long)it >> 32), c2, blk | (STREAM_NS << 16), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), x);
+    return ((unsigned long long)x[0] << 32) | x[1];
+}
+
+__device__ void block_argmax(const double *vol, int n, double &best, int &bi)
+{
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    best = -1.7976931348623157e308;
+    bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = vol[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(FULL, best, o);
+        const int oi = __shfl_down_sync(FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        best = threadIdx.x < nw ? sv[threadIdx.x] : -1.7976931348623157e308;
+        bi = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(FULL, best, o);
+            const int oi = __shfl_down_sync(FULL, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { sv[0] = best; si[0] = bi; }
+    }
+    __syncthreads();
+    best = sv[0];
+    bi = si[0];
+    __syncthreads();
+}
+
+// local MAXLOC (mpihans.py:211-212) and staging of the clone source (mpihans.py:226-229)
+__global__ void ns_pack_kernel(const hans_ns_args a)
+{
+    double best; int bi;
+    block_argmax(a.d_vol, a.nlocal, best, bi);
+    const long long it = *a.d_iter;
+    const unsigned long long K = (unsigned long long)a.nlocal * (unsigned long long)a.world;
+    const unsigned long long g = ns_draw(a.seed, it, 0u, 0u) % K; // replaces randint, mpihans.py:220
+    const int src_rank = (int)(g / (unsigned long long)a.nlocal), src = (int)(g % (unsigned long long)a.nlocal);
+    if (threadIdx.x == 0) { a.d_rec[0] = best; a.d_rec[1] = (double)bi; }
+    if (src_rank == a.rank) {
+        const int n3 = 3 * a.N;
+        if (threadIdx.x == 0) a.d_rec[2] = a.d_vol[src];
+        if (threadIdx.x < 9) a.d_rec[3 + threadIdx.x] = a.d_H[(size_t)src * 9 + threadIdx.x];
+        const double *r = a.d_R + (size_t)src * n3;
+        for (int i = threadIdx.x; i < n3; i += blockDim.x) a.d_rec[12 + i] = r[i];
+    }
+}
+
+// global MAXLOC (mpihans.py:215), ceiling, log, trajectory staging, clone (mpihans.py:232-237),
+// active walkers (mpihans.py:236-239)
+__global__ void ns_resolve_kernel(const hans_ns_args a)
+{
+    __shared__ double s_vmax;
+    __shared__ int s_rank, s_idx;
+    const int rec = 12 + 3 * a.N, n3 = 3 * a.N;
+    const long long it = *a.d_iter;
+    if (threadIdx.x == 0) {
+        double best = -1.7976931348623157e308; int br = 0, bi = 0;
+        for (int r = 0; r < a.world; ++r) {
+            const double v = a.d_gathered[(size_t)r * rec];
+            if (v > best) { best = v; br = r; bi = (int)a.d_gathered[(size_t)r * rec + 1]; }
+        }
+        s_vmax = best; s_rank = br; s_idx = bi;
+        *a.d_limit = best;
+        if (a.d_log && a.log_cap > 0) {
+            double *l = a.d_log + 3 * (size_t)(it % a.log_cap);
+            l[0] = best; l[1] = (double)br; l[2] = (double)bi;
+        }
+    }
+    __syncthreads();
+    const int mrank = s_rank, midx = s_idx;
+    const unsigned long long K = (unsigned long long)a.nlocal * (unsigned long long)a.world;
+    const unsigned long long g = ns_draw(a.seed, it, 0u, 0u) % K;
+    const int src_rank = (int)(g / (unsigned long long)a.nlocal);
+    if (mrank == a.rank) {
+        double *dr = a.d_R + (size_t)midx * n3;
+        if (a.traj_interval > 0 && a.d_traj && (it % a.traj_interval) == 0) {
+            const int slot = (int)((it / a.traj_interval) % a.traj_slots);
+            double *t = a.d_traj + (size_t)slot * rec;
+            if (threadIdx.x == 0) { t[0] = s_vmax; t[1] = (double)midx; t[2] = a.d_vol[midx]; a.d_traj_iter[slot] = it; }
+            if (threadIdx.x < 9) t[3 + threadIdx.x] = a.d_H[(size_t)midx * 9 + threadIdx.x];
+            for (int i = threadIdx.x; i < n3; i += blockDim.x) t[12 + i] = dr[i];
+            __syncthreads();
+        }
+        const double *sr = a.d_gathered + (size_t)src_rank * rec;
+        if (threadIdx.x == 0) a.d_vol[midx] = sr[2];
+        if (threadIdx.x < 9) a.d_H[(size_t)midx * 9 + threadIdx.x] = sr[3 + threadIdx.x];
+        for (int i = threadIdx.x; i < n3; i += blockDim.x) dr[i] = sr[12 + i];
+    }
+    const int nv = a.nlocal / a.nw_per_vrank;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        int id;
+        if (mrank == a.rank && midx / a.nw_per_vrank == v) id = midx;                       // mpihans.py:236
+        else id = v * a.nw_per_vrank + (int)(ns_draw(a.seed, it, (uint32_t)(a.rank * nv + v), 1u) % (unsigned)a.nw_per_vrank); // :239
+        a.d_ids[v] = id;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.d_iter = it + 1;
+}
+
 // FP32 FFMA issue-rate probe (roofline denominator)
 __global__ void ffma_kernel(int iters, float *sink)
 {
@@ -1016,6 +1136,35 @@ int hans_clone(const hans_cfg *cfg, const double *d_srcH, const double *d_srcR, 
     if (src < 0 || dst < 0) return fail(HANS_EINVAL, "negative walker index");
     clone_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(cfg->nchains * cfg->nbeads, d_srcH, d_srcR, d_srcvol, src, d_src_index,
                                                       d_dstH, d_dstR, d_dstvol, dst, d_dst_index, d_enable);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+static int check_ns(const hans_ns_args *a)
+{
+    if (!a) return fail(HANS_EINVAL, "args is NULL");
+    if (a->N < 1 || a->nlocal < 1 || a->world < 1 || a->rank < 0 || a->rank >= a->world) return fail(HANS_EINVAL, "bad sizes");
+    if (a->nw_per_vrank < 1 || a->nlocal % a->nw_per_vrank) return fail(HANS_EINVAL, "nlocal must be a multiple of nw_per_vrank");
+    if (!a->d_H || !a->d_R || !a->d_vol || !a->d_iter || !a->d_rec || !a->d_gathered || !a->d_limit || !a->d_ids)
+        return fail(HANS_EINVAL, "NULL device pointer");
+    if (a->traj_interval > 0 && a->d_traj && (a->traj_slots < 1 || !a->d_traj_iter)) return fail(HANS_EINVAL, "bad trajectory staging");
+    return HANS_OK;
+}
+
+int hans_ns_pack(const hans_ns_args *a, void *stream)
+{
+    int rc = check_ns(a);
+    if (rc) return rc;
+    ns_pack_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_ns_resolve(const hans_ns_args *a, void *stream)
+{
+    int rc = check_ns(a);
+    if (rc) return rc;
+    ns_resolve_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a);
     CK(cudaGetLastError());
     return HANS_OK;
 }

@@ -172,6 +172,51 @@ int hans_clone(const hans_cfg *cfg, const double *d_srcH, const double *d_srcR,
                double *d_dstR, double *d_dstvol, int dst, const int32_t *d_dst_index,
                const int32_t *d_enable, void *stream);
 
+/* ---- one nested-sampling iteration without host round trips (mpihans.py:210-245) ---------------
+ * The host enqueues, per iteration:  hans_ns_pack -> [all-gather of the per-rank records over
+ * NCCL when world > 1] -> hans_ns_resolve -> hans_mc_run_batch(d_ids, d_volume_limit = d_limit).
+ * Everything that varies per iteration (iteration number, clone source, active walkers, ceiling)
+ * lives in device memory, so a chunk of iterations can be enqueued (or graph-captured) without
+ * synchronising.
+ *
+ * Walkers are sharded nlocal per rank (mpihans.py:54,185); a rank may host several "virtual ranks"
+ * of nw_per_vrank walkers each, and -- exactly like one MPI rank of the reference,
+ * mpihans.py:232-241 -- every virtual rank walks ONE walker per iteration: the freshly cloned
+ * max-volume slot if it owns it, else a uniformly random one of its walkers.
+ *
+ * Record layout (doubles): [0] local max volume, [1] its local index, [2] volume of the staged
+ * clone source, [3..11] its cell, [12..12+3N) its beads.  The clone source is
+ * g = Philox(seed; iteration) mod (nlocal*world) on every rank alike (replaces the randint +
+ * bcast of mpihans.py:219-223); only the rank that owns it stages it (mpihans.py:226-229).
+ */
+typedef struct hans_ns_args {
+    int32_t N;             /* beads per walker */
+    int32_t nlocal;        /* walkers resident on this rank */
+    int32_t rank, world;
+    int32_t nw_per_vrank;  /* the reference's nwalkers (per MPI rank); nlocal % nw_per_vrank == 0 */
+    int32_t traj_interval; /* mpihans.py:38; 0 = never stage trajectory frames */
+    int32_t traj_slots;
+    int32_t log_cap;       /* entries in d_log (ring) */
+    uint64_t seed;
+    double *d_H, *d_R, *d_vol;
+    int64_t *d_iter;          /* device iteration counter; incremented by hans_ns_resolve */
+    double *d_rec;            /* this rank's record, 12 + 3N doubles */
+    const double *d_gathered; /* world records (== d_rec when world == 1) */
+    double *d_limit;          /* out: the new volume ceiling = global max volume (mpihans.py:215) */
+    double *d_log;            /* [log_cap][3]: max volume, owner rank, owner index; slot = iter % log_cap */
+    int32_t *d_ids;           /* out: [nlocal / nw_per_vrank] walkers to walk this iteration */
+    double *d_traj;           /* [traj_slots][12+3N]: the max walker BEFORE it is overwritten
+                                 (mpihans.py:232-237), staged when iter % traj_interval == 0 */
+    int64_t *d_traj_iter;     /* [traj_slots] iteration staged in each slot (-1 = empty) */
+} hans_ns_args;
+
+/* local MAXLOC (mpihans.py:211-212) + stage the clone source if this rank owns it */
+int hans_ns_pack(const hans_ns_args *a, void *stream);
+/* global MAXLOC over the gathered records (mpihans.py:215; ties -> lowest rank, then index), new
+ * ceiling, volumes log, trajectory staging, clone into the max slot (mpihans.py:232-237), active
+ * walker list (mpihans.py:236-239), iteration counter += 1 */
+int hans_ns_resolve(const hans_ns_args *a, void *stream);
+
 /* FP32 FFMA issue-rate probe used as the roofline denominator in bench.py: runs `iters`
  * dependent-chain-free FFMAs per thread on the whole chip, returns achieved TFLOP/s. */
 int hans_ffma_peak(int iters, double *tflops, void *stream);
