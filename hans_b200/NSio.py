@@ -1,0 +1,180 @@
+"""Mirror of the reference's ``NesSa.NSio``: stdin `key = value` input, restart file, extxyz
+trajectory (all file:line citations into /root/reference/NesSa/NSio.py unless noted).
+
+restart.hdf5: written with h5py when it is importable (schema of NSio.py:69-111: root attributes =
+every parameter + prev_iters + step sizes, one group per walker `walker_{rank}_{i:04d}` with
+`coordinates (N,3) f8` and `unitcell (3,3) f8`).  h5py is NOT installed in this image, so the same
+logical content is then stored as a numpy .npz container next to the requested name
+(`restart.hdf5` -> `restart.hdf5.npz`, keys `attr/<name>`, `<group>/coordinates`,
+`<group>/unitcell`); `open_restart` reads either.  This is a documented gap.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from .atoms import Atoms, read_extxyz, write_extxyz
+
+try:  # pragma: no cover - not available in the build image
+    import h5py  # type: ignore
+    HAVE_H5PY = True
+except ImportError:
+    h5py = None
+    HAVE_H5PY = False
+
+FLOAT_KEYS = ["bondlength", "bondangle", "min_angle", "min_aspect_ratio", "pressure", "upper_bound", "lower_bound", "time"]
+INT_KEYS = ["nchains", "nbeads", "nwalkers", "walklength", "initial_walk", "analyse", "equil_iter", "main_iter", "index"]
+BOOL_KEYS = ["profile"]
+# keys of this implementation (not in the reference): all optional
+EXTRA_INT_KEYS = ["seed", "ranks_per_gpu", "restart_interval", "traj_interval", "threads_per_walker"]
+
+
+def parse_hans_text(f: str) -> dict:
+    """read_hans_file's parsing (NSio.py:29-62) on a string."""
+    data = {}
+    if f == "":
+        print("Error: No input file specified")
+        sys.exit(1)
+    for line in f.split("\n"):
+        if not line.startswith('#') and line.strip() != '':
+            key, value = line.split("=", 1)
+            data[key.strip()] = value.strip()
+    for key in FLOAT_KEYS:
+        if key in data:
+            data[key] = float(data[key])
+    for key in INT_KEYS + EXTRA_INT_KEYS:
+        if key in data:
+            data[key] = int(data[key])
+    for key in BOOL_KEYS:
+        if key in data:
+            data[key] = bool(int(data[key]))
+    data.setdefault("initial_walk", 1000)
+    data.setdefault("analyse", 0)
+    data.setdefault("bondlength", 0.4)
+    data.setdefault("bondangle", 109.7)
+    data.setdefault("min_angle", 45.0)
+    data.setdefault("min_aspect_ratio", 0.8)
+    data.setdefault("restart_file", "restart.hdf5")
+    return data
+
+
+def read_hans_file(filename=None) -> dict:
+    """NSio.py:19-67: parse the input from stdin (default) or a file."""
+    if filename is None:
+        f = sys.stdin.read()
+    else:
+        with open(filename, "tr") as inp_file:
+            f = inp_file.read()
+    return parse_hans_text(f)
+
+
+# ---- restart container ------------------------------------------------------------------------------
+def _npz_name(filename: str) -> str:
+    return filename if filename.endswith(".npz") else filename + ".npz"
+
+
+def restart_exists(filename: str) -> bool:
+    return os.path.exists(filename) or os.path.exists(_npz_name(filename))
+
+
+def restart_paths(filename: str):
+    """The on-disk names a restart called `filename` may occupy."""
+    return [filename, _npz_name(filename)]
+
+
+def save_restart(filename: str, attrs: dict, walkers: dict) -> str:
+    """walkers: {groupname: (coordinates (N,3), unitcell (3,3))}.  Returns the path written."""
+    if HAVE_H5PY:  # pragma: no cover
+        with h5py.File(filename, "w") as f:
+            for k, v in attrs.items():
+                f.attrs.create(k, v)
+            for g, (coords, cell) in walkers.items():
+                grp = f.create_group(g)
+                grp.create_dataset("coordinates", data=np.asarray(coords, dtype=np.float64))
+                grp.create_dataset("unitcell", data=np.asarray(cell, dtype=np.float64))
+        return filename
+    out = {}
+    for k, v in attrs.items():
+        out["attr/" + k] = np.asarray(v)
+    for g, (coords, cell) in walkers.items():
+        out[g + "/coordinates"] = np.asarray(coords, dtype=np.float64)
+        out[g + "/unitcell"] = np.asarray(cell, dtype=np.float64)
+    path = _npz_name(filename)
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **out)
+    os.replace(tmp, path)
+    return path
+
+
+def open_restart(filename: str):
+    """Returns (attrs, walkers) as written by save_restart (either container)."""
+    if HAVE_H5PY and os.path.exists(filename):  # pragma: no cover
+        attrs, walkers = {}, {}
+        with h5py.File(filename, "r") as f:
+            for k in f.attrs:
+                attrs[k] = f.attrs[k]
+            for g in f:
+                walkers[g] = (f[g]["coordinates"][:], f[g]["unitcell"][:])
+        return attrs, walkers
+    path = _npz_name(filename)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"no restart file {filename} (or {path})")
+    attrs, walkers = {}, {}
+    with np.load(path, allow_pickle=False) as z:
+        for k in z.files:
+            if k.startswith("attr/"):
+                v = z[k]
+                attrs[k[5:]] = v.item() if v.shape == () else v
+            else:
+                g, ds = k.rsplit("/", 1)
+                walkers.setdefault(g, [None, None])[0 if ds == "coordinates" else 1] = z[k]
+    return attrs, {g: tuple(v) for g, v in walkers.items()}
+
+
+def restart_attrs(args: dict, i: int, steps: dict) -> dict:
+    """Root attributes of the restart file, NSio.py:74-83."""
+    attrs = {}
+    for j in args:
+        v = args[j]
+        if v is None:
+            continue
+        attrs[j] = v
+    attrs["prev_iters"] = i + 1
+    for k in ("dv_max", "dr_max", "dt_max", "dh_max", "dshear", "dstretch"):
+        if k in steps and steps[k] is not None:
+            attrs[k] = float(steps[k])
+    return attrs
+
+
+def write_to_restart(args, rank_states, filename="restart.hdf5", i=0, steps=None) -> str:
+    """NSio.py:69-111.  rank_states[r] = (H (nw,3,3), R (nw,N,3)) for every rank r, already gathered
+    on the writing rank (the reference ssend/recvs lists of Atoms, NSio.py:96-110)."""
+    walkers = {}
+    for r, (H, R) in enumerate(rank_states):
+        for iw in range(H.shape[0]):
+            walkers[f"walker_{r}_{iw + 1:04d}"] = (R[iw], H[iw])  # NSio.py:87, 1-based, :04d
+    return save_restart(filename, restart_attrs(args, i, steps or {}), walkers)
+
+
+def write_to_extxyz(H, R, filename="traj.extxyz"):
+    """NSio.py:113-125: wrap the configuration into the cell and append it to the trajectory."""
+    at = Atoms(f"C{len(R)}", positions=R, pbc=True, cell=H)
+    at.wrap()
+    write_extxyz(filename, at, append=True)
+
+
+def restart_cleanup(args, traj_interval=100):
+    """NSio.py:127-144: drop volumes.txt lines / trajectory frames newer than the restart point."""
+    with open("volumes.txt", "r+") as f:
+        lines = f.readlines()
+    if (len(lines) - 1) > args["prev_iters"]:
+        print("Warning, restarting from an older file, data may be overwritten/deleted")
+        lines = lines[:(args["prev_iters"] + 1)]
+        with open("volumes.txt", "w+") as f:
+            f.writelines(lines)
+        n_images = max(args["prev_iters"] // traj_interval, 1)
+        if os.path.exists("traj.extxyz"):
+            old = read_extxyz("traj.extxyz", f":{n_images}")
+            write_extxyz("traj.extxyz", old, append=False)

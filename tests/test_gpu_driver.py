@@ -1,0 +1,137 @@
+"""End-to-end checks of the host layer on a GPU: the alk / MCNS drop-in surface and the mpihans
+driver with its file contract (volumes.txt, traj.extxyz, restart)."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+ARGS = dict(nwalkers=4, nchains=8, nbeads=4, bondlength=0.4, bondangle=109.7, min_angle=45.0, min_aspect_ratio=0.8)
+
+
+def _setup_alk(seed=3):
+    from hans_b200 import MCNS as NS
+    NS.alk.random_set_random_seed(seed)
+    np.random.seed(seed)
+    NS.initialise_sim_cells(ARGS, quiet=1)
+    NS.create_initial_configs(ARGS)
+    return NS
+
+
+def test_alk_surface_and_views(oracle):
+    NS = _setup_alk()
+    alk = NS.alk
+    assert alk.alkane_get_nchains() == 8 and alk.alkane_get_nbeads() == 4
+    cell = alk.box_get_cell(1)
+    assert cell.shape == (3, 3) and np.allclose(cell, 0.999 * np.eye(3) * np.cbrt(15 * 32))
+    assert alk.box_compute_volume(2) == pytest.approx(0.999 ** 3 * 15 * 32)
+    for ibox in range(1, 5):
+        assert alk.alkane_check_chain_overlap(ibox) == 0
+    # the chain getter is a writable view of the box: writes are seen by the next native call
+    ch = alk.alkane_get_chain(3, 2)
+    assert ch.shape == (4, 3) and ch.flags.writeable
+    other = alk.alkane_get_chain(5, 2)
+    keep = ch.copy()
+    ch[:] = other + 0.01
+    assert alk.alkane_check_chain_overlap(2) == 1
+    ch[:] = keep
+    assert alk.alkane_check_chain_overlap(2) == 0
+    # box predicates agree with the Python statements of the reference (MCNS.py:97-133)
+    alk.alkane_change_box(1, np.array([[0.3, 0.1, 0.0], [0.0, -0.2, 0.4], [0.2, 0.0, 0.1]]))
+    assert alk.box_min_aspect_ratio(1) == pytest.approx(NS.min_aspect_ratio(1), rel=1e-13)
+    assert NS.min_angle(1) == pytest.approx(np.arccos(oracle.max_abs_cos(alk.box_get_cell(1))), rel=1e-12)
+    assert alk.alkane_check_chain_overlap(1) in (0, 1)
+    # bond geometry survives every move type
+    for _ in range(20):
+        b = alk.alkane_translate_chain(2, 3); assert b in (0.0, 1.0)
+        b, q = alk.alkane_rotate_chain(2, 3, 0); assert q.shape == (4,) and abs(q @ q - 1) < 1e-12
+        b, bead, ang = alk.alkane_bond_rotate(2, 3, 1); assert 4 <= bead <= 4
+    x = alk.alkane_get_chain(2, 3)
+    assert np.allclose(np.linalg.norm(np.diff(x, axis=0), axis=1), 0.4, atol=1e-12)
+    # volume move: save / propose / reset restores exactly
+    H0, R0 = alk.box_get_cell(4).copy(), alk.alkane_get_chain(1, 4).copy()
+    boltz = alk.alkane_box_resize(0.0, 4, 0)
+    assert boltz >= 0.0 and not np.array_equal(alk.box_get_cell(4), H0)
+    alk.alkane_box_resize(0.0, 4, 1)
+    assert np.array_equal(alk.box_get_cell(4), H0) and np.array_equal(alk.alkane_get_chain(1, 4), R0)
+    alk.alkane_destroy(); alk.box_destroy()
+
+
+def test_mc_run_dropin_matches_python_loop_statistically():
+    """The fused MC_run and the reference-shaped per-move loop (through the alk entry points) must
+    sample the same thing: compare acceptance rates of a fixed-volume-ceiling walk."""
+    NS = _setup_alk(seed=5)
+    mr = NS.default_move_ratio(dict(ARGS))
+    vol0 = NS.alk.box_compute_volume(1)
+    v, rate_f = NS.MC_run(ARGS, 60, mr, 1, volume_limit=vol0, min_ang=45.0, min_ar=0.8)
+    assert v <= vol0 * (1 + 1e-12) and rate_f.shape == (6,)
+    assert NS.alk.alkane_check_chain_overlap(1) == 0
+    v2, rate_p = NS.MC_run_python_loop(ARGS, 12, mr, 2, volume_limit=vol0, min_ang=45.0, min_ar=0.8)
+    assert NS.alk.alkane_check_chain_overlap(2) == 0 and v2 <= vol0 * (1 + 1e-12)
+    # translate / rotate / dihedral acceptance in the dilute start is high in both
+    for k in (1, 2, 3):
+        assert abs(rate_f[k] - rate_p[k]) < 0.15, (k, rate_f, rate_p)
+    vols = NS.perturb_initial_configs(dict(ARGS), mr, 5)
+    assert set(vols) == {1, 2, 3, 4}
+    r, dsh, dst = NS.adjust_mc_steps(dict(ARGS), NS.SingleComm(), mr, vol0, walklength=4,
+                                     min_dstep=np.full(6, 1e-10), dv_max=50.0, dr_max=50.0)
+    assert r.shape == (6,) and dsh > 0 and dst > 0
+    NS.populate_boxes_python_loop(dict(ARGS, nwalkers=1))
+    assert NS.alk.alkane_check_chain_overlap(1) == 0
+    NS.alk.alkane_destroy()
+
+
+def test_driver_files_and_restart(tmp_path, monkeypatch):
+    from hans_b200 import NSio, mpihans
+    monkeypatch.chdir(tmp_path)
+    text = """move_ratio = 3,48,32,16,3,3
+nbeads = 4
+nchains = 8
+nwalkers = 6
+ranks_per_gpu = 4
+iterations = 230
+walklength = 3
+initial_walk = 10
+directory = run1
+seed = 11
+restart_interval = 200
+"""
+    P = NSio.parse_hans_text(text)
+    mpihans.main(dict(P))
+    os.chdir(tmp_path)
+    lines = open("run1/volumes.txt").read().splitlines()
+    assert lines[0] == "24 1 32 False 8 "           # K, n_cull, dof = 8 + 3*8, flat_V_prior, nchains
+    assert len(lines) == 231
+    it = [int(l.split()[0]) for l in lines[1:]]
+    vol = np.array([float(l.split()[1]) for l in lines[1:]])
+    assert it == list(range(230)) and (np.diff(vol) <= 1e-9).all(), "ceiling must decrease monotonically"
+    assert all(l.endswith(" ") and l.split()[1] == l.split()[2] for l in lines[1:])
+    from hans_b200.atoms import read_extxyz
+    frames = read_extxyz("run1/traj.extxyz", ":")
+    assert len(frames) == 3 and len(frames[0]) == 32  # iterations 0, 100, 200
+    frac = np.linalg.solve(frames[1].cell.T, frames[1].positions.T).T
+    assert (frac > -1e-6).all() and (frac < 1 + 1e-6).all()
+    assert abs(frames[1].get_volume() - vol[100]) < 1e-6 * vol[100]
+    attrs, walkers = NSio.open_restart("run1/restart.hdf5")
+    assert attrs["prev_iters"] == 230 and len(walkers) == 24 and attrs["dv_max"] > 0
+    assert NSio.restart_exists("run1/restart_backup.hdf5")
+    assert walkers["walker_0_0001"][0].shape == (32, 3) and walkers["walker_0_0024"][1].shape == (3, 3)
+    # resume for 40 more iterations
+    P2 = NSio.parse_hans_text("from_restart = 1\ndirectory = run1\n")
+    mpihans.main(dict(P2))
+    os.chdir(tmp_path)
+    lines = open("run1/volumes.txt").read().splitlines()
+    assert len(lines) == 1 + 460 and int(lines[-1].split()[0]) == 459
+    vol = np.array([float(l.split()[1]) for l in lines[1:]])
+    assert (np.diff(vol) <= 1e-9).all()
