@@ -1,0 +1,93 @@
+"""The C-ABI library must load without a GPU and export every symbol include/hans_b200.h declares;
+struct layouts on the Python side must match the header; argument validation must not need a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hans_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hans_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hans_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/hans_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "hans_b200/_lib.py EXPORTS out of sync with the header"
+    assert _lib.lib.hans_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for n in names:
+        assert re.search(rf"\bT {n}\b", out), n
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    from hans_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "hans_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu ", sizeof(hans_cfg), sizeof(hans_proposal), sizeof(hans_decision), sizeof(hans_ns_args));
+  printf("%zu %zu %zu %zu ", offsetof(hans_cfg, dv_max), offsetof(hans_cfg, move_cum), offsetof(hans_cfg, bondlength), offsetof(hans_cfg, sin_bondangle));
+  printf("%zu %zu %zu ", offsetof(hans_proposal, p), offsetof(hans_proposal, u_acc), offsetof(hans_decision, boltz));
+  printf("%zu %zu %zu\n", offsetof(hans_ns_args, seed), offsetof(hans_ns_args, d_H), offsetof(hans_ns_args, d_traj_iter));
+  return 0; }''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.Cfg), _lib.PROPOSAL_DTYPE.itemsize, _lib.DECISION_DTYPE.itemsize, C.sizeof(_lib.NsArgs),
+            _lib.Cfg.dv_max.offset, _lib.Cfg.move_cum.offset, _lib.Cfg.bondlength.offset, _lib.Cfg.sin_bondangle.offset,
+            _lib.PROPOSAL_DTYPE.fields["p"][1], _lib.PROPOSAL_DTYPE.fields["u_acc"][1], _lib.DECISION_DTYPE.fields["boltz"][1],
+            _lib.NsArgs.seed.offset, _lib.NsArgs.d_H.offset, _lib.NsArgs.d_traj_iter.offset]
+    assert got == want
+    # the oracle's structs are laid out identically (same proposals feed both)
+    from oracle import oracle as ho
+    assert C.sizeof(ho.Cfg) == C.sizeof(_lib.Cfg) and ho.PROPOSAL_DTYPE == _lib.PROPOSAL_DTYPE
+
+
+def test_host_side_entry_points_and_validation():
+    from hans_b200 import _lib
+    L = _lib.lib
+    assert L.hans_moves_per_sweep(6, 16) == 87 and L.hans_moves_per_sweep(1, 64) == 71    # MCNS.py:296-301
+    cfg = _lib.make_cfg(16, 6, [3, 48, 32, 0, 3, 3])
+    assert list(cfg.move_cum)[-1] == 1.0 and abs(cfg.move_cum[0] - 3 / 89) < 1e-15
+    assert L.hans_walker_smem_bytes(C.byref(cfg)) == (6 * 96 + 18 + 36) * 8
+    assert L.hans_default_threads_per_walker(C.byref(cfg)) == 32
+    big = _lib.make_cfg(128, 6, [1, 384, 256, 384, 3, 3])
+    assert L.hans_default_threads_per_walker(C.byref(big)) == 256
+    # argument errors are reported as codes + text, never by exiting, and need no GPU
+    assert L.hans_mc_run_batch(None, None, None, None, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 0, None) == -1
+    assert b"cfg" in L.hans_last_error()
+    bad = _lib.make_cfg(4, 100, [1, 1, 1, 1, 1, 1])
+    assert L.hans_check_overlap(C.byref(bad), 1, 1, None, 1, 0, 1, 0, None) == -3          # HANS_ELIMIT: nbeads > 64
+    assert L.hans_replay(C.byref(cfg), 1, 1, None, 1, 1, 1, 0.0, 7, 1, 0, None) == -1       # bad mode
+    assert L.hans_mc_run_batch(C.byref(cfg), 1, 1, 1, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 48, None) == -1
+    with pytest.raises(_lib.HansError):
+        _lib.check(-1)
+    with pytest.raises(Exception):
+        _lib.make_cfg(4, 2, [1, 2, 3])                                                      # MCNS.py:614-615
+    assert L.hans_device_count() >= 0
+
+
+def test_no_product_module_touches_the_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "hans_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r"CPU checker", "", text).lower() or f in (), (
+                    f"{f} mentions the oracle")
