@@ -168,8 +168,7 @@ __device__ __forceinline__ void box_muller(double ua, double ub, double &z1, dou
 // ---------------------------------------------------------------------------------------------
 // One proposal (registers).  Draw order of the self-driving mode, SURVEY.md 10.1: per move four
 // Philox blocks keyed (seed; ctr, walker id): blk0 = {u_chain, u_type}, blk1 = {u1,u2},
-// blk2 = {u3,u4}, blk3 = {u_acc, spare}.  The four blocks are computed by four neighbouring
-// lanes and exchanged by shuffle, so every lane of the walker's warp(s) ends with the same record.
+// blk2 = {u3,u4}, blk3 = {u_acc, spare}.
 // ---------------------------------------------------------------------------------------------
 struct Prop {
     int type, ichain, idx0, idx1;
@@ -179,18 +178,16 @@ struct Prop {
 
 __device__ __noinline__ Prop gen_proposal(const hans_cfg &c, uint64_t seed, uint32_t gid, uint64_t ctr)
 {
-    const int wl = threadIdx.x & 31;
-    double ua, ub;
-    draw_block(seed, (uint32_t)ctr, (uint32_t)(ctr >> 32), gid, (uint32_t)(wl & 3), STREAM_MOVE, ua, ub);
-    const int base = wl & ~3;
-    const double u_chain = __shfl_sync(FULL, ua, base + 0);
-    const double u_type = __shfl_sync(FULL, ub, base + 0);
-    const double u1 = __shfl_sync(FULL, ua, base + 1);
-    const double u2 = __shfl_sync(FULL, ub, base + 1);
-    const double u3 = __shfl_sync(FULL, ua, base + 2);
-    const double u4 = __shfl_sync(FULL, ub, base + 2);
+    // every lane generates the proposal of a DIFFERENT move (ctr differs per lane): the scalar work
+    // of a batch of moves is spread over the lanes of the walker's group
+    const uint32_t lo = (uint32_t)ctr, hi = (uint32_t)(ctr >> 32);
+    double u_chain, u_type, u1, u2, u3, u4, u_acc, spare;
+    draw_block(seed, lo, hi, gid, 0u, STREAM_MOVE, u_chain, u_type);
+    draw_block(seed, lo, hi, gid, 1u, STREAM_MOVE, u1, u2);
+    draw_block(seed, lo, hi, gid, 2u, STREAM_MOVE, u3, u4);
+    draw_block(seed, lo, hi, gid, 3u, STREAM_MOVE, u_acc, spare);
     Prop o;
-    o.u_acc = __shfl_sync(FULL, ua, base + 3);
+    o.u_acc = u_acc;
     o.p[0] = o.p[1] = o.p[2] = o.p[3] = 0.0;
     o.idx0 = o.idx1 = 0;
 
