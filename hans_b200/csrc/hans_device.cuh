@@ -176,8 +176,9 @@ struct Prop {
     double u_acc;
 };
 
-__device__ __noinline__ Prop gen_proposal(const hans_cfg &c, uint64_t seed, uint32_t gid, uint64_t ctr)
+__device__ __noinline__ Prop gen_proposal(const hans_cfg *cp, uint64_t seed, uint32_t gid, uint64_t ctr)
 {
+    const hans_cfg &c = *cp;
     // every lane generates the proposal of a DIFFERENT move (ctr differs per lane): the scalar work
     // of a batch of moves is spread over the lanes of the walker's group
     const uint32_t lo = (uint32_t)ctr, hi = (uint32_t)(ctr >> 32);

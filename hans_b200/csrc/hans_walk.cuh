@@ -1,0 +1,910 @@
+// hans_walk.cuh -- the walker kernels (sm_100a): MC_run for a batch of walkers, the overlap
+// predicate, alkane_change_box and chain growth.
+//
+// Execution model: one WALKER per thread group of T threads (T = 32: one warp per walker, four
+// walkers per CTA; T = 64/128/256: one CTA per walker).  A walker stays in SHARED MEMORY for its
+// whole walk:
+//     P   [3N] f64   current beads, x y z interleaved (same layout as the restart file / HBM)
+//     TP  [3N] f64   trial beads of a box move (so a rejected volume move restores exactly)
+//     CN  [3nb] f64  trial chain of a single-chain move
+//     SH  [36] f64   H, H^-1, trial H, trial H^-1
+//     F4  [N] float4, G4 [N] float4, C4 [nb] float4   float32 shadows (wrapped fractional
+//                    coordinates) of P, TP, CN for the pair-test pre-filter
+//     SF  [16] f32   pre-filter parameters for H and for the trial H
+//     ring[T] 64 B   proposals of the current batch of T moves
+// All shared-memory accesses go through the one `extern __shared__` symbol with integer offsets
+// (never through pointers stored in structs), so they compile to LDS/STS and the per-walker
+// context is a handful of integers in registers.  The hot path (single-chain moves) is inlined
+// and small; box moves (a few percent of the moves, but O(N^2)) are out-of-line functions that
+// receive the context by value.
+//
+// Reference call sites replaced: NesSa/MCNS.py:276-392 (MC_run) and every alk.* call inside it.
+#pragma once
+
+#include "hans_device.cuh"
+
+namespace hb {
+
+extern __shared__ double smem[];
+#define SMF (reinterpret_cast<float *>(smem))
+#define SM4 (reinterpret_cast<float4 *>(smem))
+
+// ---------------------------------------------------------------------------------------------
+// group primitives
+// ---------------------------------------------------------------------------------------------
+template <int T> __device__ __forceinline__ void gsync()
+{
+    if (T == 32) __syncwarp(); else __syncthreads();
+}
+template <int T> __device__ __forceinline__ bool gany(bool p)
+{
+    if (T == 32) return __any_sync(FULL, p);
+    return __syncthreads_or(p ? 1 : 0) != 0;
+}
+template <int T> __host__ __device__ constexpr int cta_threads() { return T == 32 ? 128 : T; }
+
+// one proposal as it sits in the shared-memory ring (same 64-byte layout as hans_proposal)
+struct __align__(16) PropRec {
+    int type, ichain, idx0, idx1;
+    double p[4];
+    double u_acc;
+    double pad;
+};
+static_assert(sizeof(PropRec) == 64 && sizeof(hans_proposal) == 64, "proposal record layout");
+
+// per-walker context: offsets into shared memory, kept in registers
+struct WCtx {
+    int N, nb, nc, nex, npc, lane;
+    int D0;   // double index of P; TP = D0+3N, CN = D0+6N, SH = D0+6N+3nb
+    int Q0;   // float4 index of F4; G4 = Q0+N, C4 = Q0+2N; SF (floats) = 4*(Q0+2N+nb)
+    int ring; // PropRec index (64-byte units from the start of shared memory)
+    int itab; // uchar2 index of the intra-chain pair table
+    int cfg;  // double index of the CTA's copy of hans_cfg
+};
+#define W_P(w) ((w).D0)
+#define W_TP(w) ((w).D0 + 3 * (w).N)
+#define W_CN(w) ((w).D0 + 6 * (w).N)
+#define W_SH(w) ((w).D0 + 6 * (w).N + 3 * (w).nb)
+#define W_F4(w) ((w).Q0)
+#define W_G4(w) ((w).Q0 + (w).N)
+#define W_C4(w) ((w).Q0 + 2 * (w).N)
+#define W_SF(w) (4 * ((w).Q0 + 2 * (w).N + (w).nb))
+#define W_RING(w) (reinterpret_cast<PropRec *>(smem) + (w).ring)
+#define W_ITAB(w) (reinterpret_cast<const uchar2 *>(smem) + (w).itab)
+#define W_CFG(w) (reinterpret_cast<const hans_cfg *>(smem + (w).cfg))
+
+__host__ __device__ inline int intra_pairs_per_chain(int nb, int nex)
+{
+    const int m = nb - nex - 1;
+    return m > 0 ? m * (m + 1) / 2 : 0;
+}
+
+// bytes of shared memory one walker group of T threads needs (multiple of 64)
+__host__ __device__ inline size_t walker_smem_bytes(int N, int nb, int T)
+{
+    size_t b = sizeof(double) * ((size_t)6 * N + (size_t)3 * nb + 36);
+    b = (b + 15) & ~(size_t)15;
+    b += 16 * ((size_t)2 * N + nb) + 64; // float4 shadows + SF
+    b = (b + 63) & ~(size_t)63;
+    b += 64 * (size_t)T;                 // ring
+    return b;
+}
+__host__ __device__ inline size_t cta_extra_bytes(int nb, int nex)
+{
+    size_t b = ((sizeof(hans_cfg) + 15) & ~(size_t)15);
+    b += (((size_t)intra_pairs_per_chain(nb, nex) * sizeof(uchar2)) + 15) & ~(size_t)15;
+    return b;
+}
+
+template <int T>
+__device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
+{
+    constexpr int GPC = cta_threads<T>() / T;
+    WCtx w;
+    w.nb = c.nbeads; w.nc = c.nchains; w.N = c.nbeads * c.nchains; w.nex = c.nexclude;
+    w.npc = intra_pairs_per_chain(w.nb, w.nex);
+    w.lane = threadIdx.x % T;
+    const int g = threadIdx.x / T;
+    const int per = (int)walker_smem_bytes(w.N, w.nb, T);
+    const int base = per * g;                                           // bytes
+    w.D0 = base / 8;
+    const int dbytes = ((8 * (6 * w.N + 3 * w.nb + 36)) + 15) & ~15;
+    w.Q0 = (base + dbytes) / 16;
+    w.ring = (base + per - 64 * T) / 64;
+    const int extra = per * GPC;
+    w.cfg = extra / 8;
+    w.itab = (extra + (int)((sizeof(hans_cfg) + 15) & ~(size_t)15)) / 2;
+    // CTA-wide: copy of the configuration and the intra-chain pair table (ordered by b, then j)
+    {
+        const double *src = reinterpret_cast<const double *>(&c);
+        for (int i = threadIdx.x; i < (int)(sizeof(hans_cfg) / 8); i += blockDim.x) smem[w.cfg + i] = src[i];
+        uchar2 *tab = reinterpret_cast<uchar2 *>(smem) + w.itab;
+        for (int e = threadIdx.x; e < w.npc; e += blockDim.x) {
+            int b = w.nex + 1, acc = 0;
+            while (acc + (b - w.nex) <= e) { acc += b - w.nex; ++b; }
+            tab[e] = make_uchar2((unsigned char)(e - acc), (unsigned char)b);
+        }
+    }
+    __syncthreads();
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float32 pre-filter of the pair test.
+//
+// The decision "r^2 < 1" is always the float64 one (pair_r2, the arithmetic of the CPU checker).
+// To reach it cheaply, every bead also has a float32 shadow: its fractional coordinates wrapped
+// to [-0.5, 0.5].  For a pair, ds = s_j - s_i is wrapped again and r^2 = ds.G.ds is evaluated
+// with the metric tensor G = H H^T in float32 (21 operations instead of 32 float64 ones).  If the
+// result is outside the band [1 - eps, 1 + eps] the float64 test is guaranteed to agree and is
+// skipped; pairs inside the band (probability ~1e-4) are re-tested in float64.
+//
+// eps bounds |r2_f32 - r2_f64| for pairs near contact: inputs carry <= 1.5 * 2^-24 per fractional
+// component (two stored roundings + one subtraction), which moves r^2 by <= 2 |G ds| . |d(ds)|
+// <= 9 Lmax 2^-24 |d|; the nine float32 operations and the rounding of G add <= ~10 * 2^-24 times
+// the sum of |terms| <= (sum_i L_i / w_i)^2 |d|^2 (L_i cell vector lengths, w_i perpendicular widths).
+// eps = 2^-24 (16 Lmax + 16 q^2 + 64) * 1.01 carries a further safety factor.  The filter is
+// switched off (every pair is re-tested in float64) when a perpendicular width is <= 2.1, where
+// float32 and float64 could wrap a pair to different images that both lie within reach of sigma.
+// SF layout: g00, g11, g22, 2 g01, 2 g02, 2 g12, lo = 1 - eps, hi = 1 + eps.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void filter_params(int sh, int sf, bool writer)
+{
+    const double *H = smem + sh, *Hi = smem + sh + 9;
+    const double g00 = dot3(H, H), g11 = dot3(H + 3, H + 3), g22 = dot3(H + 6, H + 6);
+    const double g01 = dot3(H, H + 3), g02 = dot3(H, H + 6), g12 = dot3(H + 3, H + 6);
+    const double L0 = sqrt(g00), L1 = sqrt(g11), L2 = sqrt(g22);
+    const double b0 = sqrt((Hi[0] * Hi[0] + Hi[3] * Hi[3]) + Hi[6] * Hi[6]);
+    const double b1 = sqrt((Hi[1] * Hi[1] + Hi[4] * Hi[4]) + Hi[7] * Hi[7]);
+    const double b2 = sqrt((Hi[2] * Hi[2] + Hi[5] * Hi[5]) + Hi[8] * Hi[8]);
+    const double Lmax = fmax(L0, fmax(L1, L2));
+    const double bmax = fmax(b0, fmax(b1, b2)); // 1 / smallest perpendicular width
+    const double q = (L0 * b0 + L1 * b1) + L2 * b2;
+    const double eps = 5.9604644775390625e-8 * ((16.0 * Lmax + 16.0 * q * q) + 64.0) * 1.01;
+    float lo = (float)(1.0 - eps), hi = (float)(1.0 + eps);
+    if (!(bmax * 2.1 < 1.0) || !(eps < 0.05)) { lo = -1.0f; hi = 3.0e38f; } // filter off
+    if (writer) {
+        float *o = SMF + sf;
+        o[0] = (float)g00; o[1] = (float)g11; o[2] = (float)g22;
+        o[3] = (float)(2.0 * g01); o[4] = (float)(2.0 * g02); o[5] = (float)(2.0 * g12);
+        o[6] = lo; o[7] = hi;
+    }
+}
+
+struct Filt { float g00, g11, g22, g01, g02, g12, lo, hi; };
+__device__ __forceinline__ Filt load_filt(int sf)
+{
+    const float4 a = SM4[sf / 4], b = SM4[sf / 4 + 1];
+    Filt f;
+    f.g00 = a.x; f.g11 = a.y; f.g22 = a.z; f.g01 = a.w; f.g02 = b.x; f.g12 = b.y; f.lo = b.z; f.hi = b.w;
+    return f;
+}
+
+__device__ __forceinline__ float rint32(float x)
+{
+    const float magic = 12582912.0f; // 1.5 * 2^23
+    return __fsub_rn(__fadd_rn(x, magic), magic);
+}
+
+// float32 r^2 of a fractional difference (wrapped here)
+__device__ __forceinline__ float r2_f32(const Filt &f, float dx, float dy, float dz)
+{
+    dx = __fsub_rn(dx, rint32(dx));
+    dy = __fsub_rn(dy, rint32(dy));
+    dz = __fsub_rn(dz, rint32(dz));
+    const float t0 = __fmaf_rn(f.g02, dz, __fmaf_rn(f.g01, dy, __fmul_rn(f.g00, dx)));
+    const float t1 = __fmaf_rn(f.g12, dz, __fmul_rn(f.g11, dy));
+    const float t2 = __fmul_rn(f.g22, dz);
+    return __fmaf_rn(dx, t0, __fmaf_rn(dy, t1, __fmul_rn(dz, t2)));
+}
+
+// wrapped fractional coordinates of a Cartesian point, rounded to float32
+__device__ __forceinline__ float4 shadow_of(double x, double y, double z, const double *Hi)
+{
+    double s0, s1, s2;
+    vecmat(x, y, z, Hi, s0, s1, s2);
+    return make_float4((float)(s0 - hd_rint(s0)), (float)(s1 - hd_rint(s1)), (float)(s2 - hd_rint(s2)), 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-chain moves: the hot path
+// ---------------------------------------------------------------------------------------------
+struct Dec { int accepted, reason; double boltz; };
+__device__ __forceinline__ Dec mkdec(int a, int r, double b) { Dec d; d.accepted = a; d.reason = r; d.boltz = b; return d; }
+
+// float64 re-test of the pairs of the trial chain that fell into the band (cold)
+template <int T>
+__device__ __noinline__ bool recheck_chain_exact(WCtx w, int ichain, int b0, bool amb_inter, bool amb_intra)
+{
+    const int nb = w.nb, c0 = ichain * nb, sh = W_SH(w), cn = W_CN(w), p = W_P(w);
+    bool ov = false;
+    if (amb_inter) {
+        for (int j = w.lane; j < w.N; j += T) {
+            if ((unsigned)(j - c0) < (unsigned)nb) continue;
+            for (int b = b0; b < nb; ++b)
+                ov |= pair_r2(smem + sh, smem + sh + 9, smem[p + 3 * j] - smem[cn + 3 * b],
+                              smem[p + 3 * j + 1] - smem[cn + 3 * b + 1], smem[p + 3 * j + 2] - smem[cn + 3 * b + 2]) < 1.0;
+        }
+    }
+    if (amb_intra) {
+        const uchar2 *tab = W_ITAB(w);
+        for (int e = w.lane; e < w.npc; e += T) {
+            const uchar2 jb = tab[e];
+            if ((int)jb.y >= b0)
+                ov |= pair_r2(smem + sh, smem + sh + 9, smem[cn + 3 * jb.y] - smem[cn + 3 * jb.x],
+                              smem[cn + 3 * jb.y + 1] - smem[cn + 3 * jb.x + 1], smem[cn + 3 * jb.y + 2] - smem[cn + 3 * jb.x + 2]) < 1.0;
+        }
+    }
+    return ov;
+}
+
+// Does the trial chain (CN / C4) overlap anything?  beads [b0, nb) against every bead of every
+// other chain, and (dihedral only) the intra-chain pairs (j, b), b >= b0, beyond the exclusion.
+template <int T>
+__device__ __forceinline__ bool chain_overlaps(const WCtx &w, int ichain, int b0, bool intra, unsigned &pairs)
+{
+    const Filt f = load_filt(W_SF(w));
+    const int nb = w.nb, c0 = ichain * nb, f4 = W_F4(w), c4 = W_C4(w);
+    bool ov = false, amb = false;
+    for (int j0 = 0; j0 < w.N; j0 += T) {
+        const int j = j0 + w.lane;
+        if (j < w.N && (unsigned)(j - c0) >= (unsigned)nb) {
+            const float4 s = SM4[f4 + j];
+            for (int b = b0; b < nb; ++b) {
+                const float4 c = SM4[c4 + b];
+                const float r2 = r2_f32(f, s.x - c.x, s.y - c.y, s.z - c.z);
+                ov |= (r2 < f.lo);
+                amb |= !(r2 > f.hi);
+            }
+            pairs += (unsigned)(nb - b0);
+        }
+        if (j0 + T < w.N && gany<T>(ov)) return true; // early exit between passes
+    }
+    bool amb_intra = false;
+    if (intra) {
+        const uchar2 *tab = W_ITAB(w);
+        for (int e = w.lane; e < w.npc; e += T) {
+            const uchar2 jb = tab[e];
+            if ((int)jb.y >= b0) {
+                const float4 p = SM4[c4 + jb.x], q = SM4[c4 + jb.y];
+                const float r2 = r2_f32(f, q.x - p.x, q.y - p.y, q.z - p.z);
+                ov |= (r2 < f.lo);
+                amb_intra |= !(r2 > f.hi);
+                pairs += 1;
+            }
+        }
+    }
+    if (gany<T>(ov)) return true;
+    // nothing overlaps for certain; any pair inside the band decides in float64
+    const bool any_inter = gany<T>(amb), any_intra = intra && gany<T>(amb_intra);
+    if (any_inter || any_intra)
+        return gany<T>(recheck_chain_exact<T>(w, ichain, b0, amb, amb_intra));
+    return false;
+}
+
+// translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
+// alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
+template <int T>
+__device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int mode, unsigned &pairs)
+{
+    const int nb = w.nb, type = p->type, ichain = p->ichain;
+    const int c0 = ichain * nb, P = W_P(w) + 3 * c0, cn = W_CN(w), c4 = W_C4(w), sh = W_SH(w);
+    int b0 = 0;
+    bool intra = false;
+    if (type == HANS_TRANS) {
+        for (int b = w.lane; b < nb; b += T) {
+            const double x = smem[P + 3 * b] + p->p[0], y = smem[P + 3 * b + 1] + p->p[1], z = smem[P + 3 * b + 2] + p->p[2];
+            smem[cn + 3 * b] = x; smem[cn + 3 * b + 1] = y; smem[cn + 3 * b + 2] = z;
+            SM4[c4 + b] = shadow_of(x, y, z, smem + sh + 9);
+        }
+    } else if (type == HANS_ROT) {
+        double com[3] = {0.0, 0.0, 0.0};
+        for (int b = 0; b < nb; ++b) { com[0] += smem[P + 3 * b]; com[1] += smem[P + 3 * b + 1]; com[2] += smem[P + 3 * b + 2]; }
+        const double dn = (double)nb;
+        com[0] /= dn; com[1] /= dn; com[2] /= dn;
+        for (int b = w.lane; b < nb; b += T) {
+            const double v[3] = {smem[P + 3 * b] - com[0], smem[P + 3 * b + 1] - com[1], smem[P + 3 * b + 2] - com[2]};
+            double o[3];
+            quat_rot(p->p, v, o);
+            const double x = o[0] + com[0], y = o[1] + com[1], z = o[2] + com[2];
+            smem[cn + 3 * b] = x; smem[cn + 3 * b + 1] = y; smem[cn + 3 * b + 2] = z;
+            SM4[c4 + b] = shadow_of(x, y, z, smem + sh + 9);
+        }
+    } else {
+        const int ia = p->idx0;
+        if (nb < 4 || ia < 3 || ia > nb - 1) return mkdec(0, HANS_REJ_INVALID, 0.0);
+        const bool flip = p->idx1 != 0;
+        const int iv = P + 3 * (flip ? nb - 1 - (ia - 1) : ia - 1);
+        const int iw = P + 3 * (flip ? nb - 1 - (ia - 2) : ia - 2);
+        const double piv[3] = {smem[iv], smem[iv + 1], smem[iv + 2]};
+        double ax[3] = {piv[0] - smem[iw], piv[1] - smem[iw + 1], piv[2] - smem[iw + 2]};
+        const double n = sqrt(dot3(ax, ax));
+        ax[0] /= n; ax[1] /= n; ax[2] /= n;
+        double s, co;
+        hd_sincos(0.5 * p->p[0], &s, &co);
+        const double q[4] = {co, s * ax[0], s * ax[1], s * ax[2]};
+        for (int b = w.lane; b < nb; b += T) {
+            const int src = P + 3 * (flip ? nb - 1 - b : b);
+            double r[3] = {smem[src], smem[src + 1], smem[src + 2]};
+            if (b >= ia) {
+                const double v[3] = {r[0] - piv[0], r[1] - piv[1], r[2] - piv[2]};
+                double o[3];
+                quat_rot(q, v, o);
+                r[0] = o[0] + piv[0]; r[1] = o[1] + piv[1]; r[2] = o[2] + piv[2];
+            }
+            smem[cn + 3 * b] = r[0]; smem[cn + 3 * b + 1] = r[1]; smem[cn + 3 * b + 2] = r[2];
+            SM4[c4 + b] = shadow_of(r[0], r[1], r[2], smem + sh + 9);
+        }
+        b0 = ia;
+        intra = true;
+    }
+    gsync<T>();
+    const bool ov = chain_overlaps<T>(w, ichain, b0, intra, pairs);
+    const double boltz = ov ? 0.0 : 1.0;
+    if ((mode == HANS_MODE_PROPOSE) || (p->u_acc < boltz)) { // MCNS.py:372
+        const int f4 = W_F4(w) + c0;
+        for (int b = w.lane; b < nb; b += T) {
+            smem[P + 3 * b] = smem[cn + 3 * b]; smem[P + 3 * b + 1] = smem[cn + 3 * b + 1]; smem[P + 3 * b + 2] = smem[cn + 3 * b + 2];
+            SM4[f4 + b] = SM4[c4 + b];
+        }
+    }
+    gsync<T>();
+    return mkdec(ov ? 0 : 1, ov ? HANS_REJ_OVERLAP : HANS_ACCEPT, boltz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// box moves (cold: out of line, context by value)
+// ---------------------------------------------------------------------------------------------
+// all pairs of the TRIAL beads: bead-level round robin.  Lane owns bead i (registers) and walks
+// the offsets d = 1..N/2 with j = (i + d) mod N, so a warp reads consecutive shared-memory words
+// and every unordered pair is visited once (for even N the antipodal offset is taken by the lower
+// half only).  Same-chain pairs are skipped unless with_intra and further apart than nexclude.
+template <int T>
+__device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
+{
+    const Filt f = load_filt(W_SF(w) + 8);
+    const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18;
+    const bool even = (N & 1) == 0;
+    const int RB = T < N ? T : N;
+    const int DG = T < N ? 1 : T / N;
+    const int li = w.lane % RB, dg = w.lane / RB;
+    const bool lane_on = dg < DG;
+    bool ov = false;
+    constexpr int U = 4;
+    for (int i0 = 0; i0 < N; i0 += RB) {
+        const int i = i0 + li;
+        const bool row_on = lane_on && i < N;
+        const int ii = row_on ? i : 0;
+        const float4 si = SM4[g4 + ii];
+        const int c0 = (ii / nb) * nb, c1 = c0 + nb;
+        for (int d0 = 1; d0 <= half; d0 += DG * U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int d = d0 + u * DG + dg;
+                if (row_on && d <= half && !(even && d == half && i >= half)) {
+                    int j = i + d;
+                    if (j >= N) j -= N;
+                    const bool same = (j >= c0) && (j < c1);
+                    const int sep = j > i ? j - i : i - j;
+                    if (!same || (with_intra && sep > w.nex)) {
+                        const float4 sj = SM4[g4 + j];
+                        const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
+                        if (r2 < f.lo) ov = true;
+                        else if (!(r2 > f.hi))
+                            ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * j] - smem[tp + 3 * i],
+                                          smem[tp + 3 * j + 1] - smem[tp + 3 * i + 1], smem[tp + 3 * j + 2] - smem[tp + 3 * i + 2]) < 1.0;
+                        pairs += 1;
+                    }
+                }
+            }
+            if (gany<T>(ov)) return true;
+        }
+    }
+    return false;
+}
+
+// chains follow a cell change rigidly (first bead keeps its fractional coordinates): beads at
+// `src` under Hi_old -> beads at `dst` under H_new, and their float32 shadows under Hi_new
+template <int T>
+__device__ __forceinline__ void follow_cell(const WCtx &w, int src, int dst, int dst4, const double *Hi_old,
+                                            const double *H_new, const double *Hi_new)
+{
+    for (int i = w.lane; i < w.N; i += T) {
+        const int a = src + 3 * ((i / w.nb) * w.nb);
+        const double ax = smem[a], ay = smem[a + 1], az = smem[a + 2];
+        double f0, f1, f2, n0, n1, n2;
+        vecmat(ax, ay, az, Hi_old, f0, f1, f2);
+        vecmat(f0, f1, f2, H_new, n0, n1, n2);
+        const double x = smem[src + 3 * i] + (n0 - ax), y = smem[src + 3 * i + 1] + (n1 - ay), z = smem[src + 3 * i + 2] + (n2 - az);
+        smem[dst + 3 * i] = x; smem[dst + 3 * i + 1] = y; smem[dst + 3 * i + 2] = z;
+        SM4[dst4 + i] = shadow_of(x, y, z, Hi_new);
+    }
+}
+
+template <int T> __device__ __forceinline__ void commit_trial(const WCtx &w)
+{
+    const int p = W_P(w), tp = W_TP(w), f4 = W_F4(w), g4 = W_G4(w), sh = W_SH(w), sf = W_SF(w);
+    for (int i = w.lane; i < 3 * w.N; i += T) smem[p + i] = smem[tp + i];
+    for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = SM4[g4 + i];
+    if (w.lane < 18) smem[sh + w.lane] = smem[sh + 18 + w.lane];
+    if (w.lane < 8) SMF[sf + w.lane] = SMF[sf + 8 + w.lane];
+    gsync<T>();
+}
+
+struct DecP { int accepted, reason; double boltz; unsigned pairs; };
+
+// alk.alkane_box_resize(pressure, ibox, 0) + acceptance (MCNS.py:318,349-357), and
+// box_shear_step (MCNS.py:135-207) / box_stretch_step (MCNS.py:209-252) + accept or revert by -dH
+// (MCNS.py:360-368).  The trial lives in TP, so a rejected volume move restores the saved cell and
+// chains exactly for free.
+template <int T>
+__device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mode)
+{
+    const PropRec *p = W_RING(w) + q;
+    const hans_cfg *c = W_CFG(w);
+    const int sh = W_SH(w);
+    DecP out;
+    out.accepted = 0; out.reason = HANS_REJ_INVALID; out.boltz = 0.0; out.pairs = 0;
+    double H[9], Hn[9], Hin[9], dH[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { H[k] = smem[sh + k]; dH[k] = 0.0; }
+    const bool is_vol = p->type == HANS_VOL;
+    double boltz_f = 1.0;
+    if (is_vol) {
+        const double vol = fabs(det3(H));
+        const double vnew_t = vol + p->p[0];
+        if (!(vnew_t > 0.0)) return out;
+        const double ratio = vnew_t / vol;
+        const double s = hd_cbrt(ratio);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Hn[k] = H[k] * s;
+        const double new_volume = fabs(det3(Hn)); // MCNS.py:350
+        boltz_f = hd_exp(-c->pressure * p->p[0] + (double)c->nchains * hd_log(ratio)); // MCNS.py:266
+        out.boltz = boltz_f;
+        if (mode == HANS_MODE_FUSED) {
+            // conjunction of MCNS.py:351 evaluated cheapest-first; the O(N^2) overlap test is last
+            if (!((new_volume - volume_limit) < 2.2204460492503131e-16)) { out.reason = HANS_REJ_CEILING; return out; }
+            if (!(p->u_acc < boltz_f)) { out.reason = HANS_REJ_BOLTZ; return out; }
+        }
+    } else {
+        if (p->type == HANS_SHEAR) {
+            const int k = p->idx0;
+            const int o0 = (k == 0) ? 1 : 0;
+            const int o1 = (k == 2) ? 1 : 2;
+            double v1[3] = {H[3 * o0], H[3 * o0 + 1], H[3 * o0 + 2]};
+            double v2[3] = {H[3 * o1], H[3 * o1 + 1], H[3 * o1 + 2]};
+            const double n1 = sqrt(dot3(v1, v1));
+            v1[0] /= n1; v1[1] /= n1; v1[2] /= n1;
+            const double pr = dot3(v1, v2);
+            v2[0] -= v1[0] * pr; v2[1] -= v1[1] * pr; v2[2] -= v1[2] * pr;
+            const double n2 = sqrt(dot3(v2, v2));
+            v2[0] /= n2; v2[1] /= n2; v2[2] /= n2;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double nw = H[3 * k + a] + (p->p[0] * v1[a] + p->p[1] * v2[a]);
+                dH[3 * k + a] = nw - H[3 * k + a];
+            }
+        } else {
+            const int i = p->idx0, j = p->idx1;
+            const double e1 = hd_exp(p->p[0]), e2 = hd_exp(-p->p[0]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                dH[3 * i + a] = H[3 * i + a] * e1 - H[3 * i + a];
+                dH[3 * j + a] = H[3 * j + a] * e2 - H[3 * j + a];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Hn[k] = H[k] + dH[k];
+    }
+    hinv(Hn, Hin);
+    follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), smem + sh + 9, Hn, Hin); // alk.alkane_change_box, MCNS.py:186,238
+    if (w.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { smem[sh + 18 + k] = Hn[k]; smem[sh + 27 + k] = Hin[k]; }
+    }
+    gsync<T>();
+    filter_params(sh + 18, W_SF(w) + 8, w.lane == 0);
+    gsync<T>();
+    int reason = HANS_ACCEPT;
+    if (is_vol) {
+        if (trial_overlap<T>(w, false, out.pairs)) reason = HANS_REJ_OVERLAP;
+        if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) commit_trial<T>(w);
+        out.accepted = reason == HANS_ACCEPT; out.reason = reason; out.boltz = reason == HANS_ACCEPT ? boltz_f : 0.0;
+        return out;
+    }
+    if (min_aspect_ratio(Hn) < c->min_ar) reason = HANS_REJ_ASPECT;               // MCNS.py:194,243
+    else if (max_abs_cos(Hn) > c->cos_min_ang) reason = HANS_REJ_ANGLE;           // MCNS.py:196,245
+    else if (trial_overlap<T>(w, true, out.pairs)) reason = HANS_REJ_OVERLAP;     // MCNS.py:198,247
+    if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
+        commit_trial<T>(w);
+    } else {
+        // MCNS.py:366-368: the reference reverts by applying -dH through alkane_change_box, which
+        // is not an exact restore; reproduce that arithmetic from the trial state.
+        double H2[9], H2i[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H2[k] = Hn[k] + (-1.0 * dH[k]);
+        hinv(H2, H2i);
+        follow_cell<T>(w, W_TP(w), W_P(w), W_F4(w), Hin, H2, H2i);
+        if (w.lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { smem[sh + k] = H2[k]; smem[sh + 9 + k] = H2i[k]; }
+        }
+        gsync<T>();
+        filter_params(sh, W_SF(w), w.lane == 0);
+        gsync<T>();
+    }
+    out.accepted = reason == HANS_ACCEPT; out.reason = reason; out.boltz = reason == HANS_ACCEPT ? 1.0 : 0.0;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state load / store
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, const double *gR, int wi, bool shadows)
+{
+    const double *r = gR + (size_t)wi * w.N * 3;
+    const int p = W_P(w), sh = W_SH(w);
+    for (int i = w.lane; i < 3 * w.N; i += T) smem[p + i] = r[i];
+    double H[9], Hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = gH[(size_t)wi * 9 + k];
+    hinv(H, Hi);
+    if (w.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { smem[sh + k] = H[k]; smem[sh + 9 + k] = Hi[k]; }
+    }
+    gsync<T>();
+    if (shadows) {
+        const int f4 = W_F4(w);
+        for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = shadow_of(smem[p + 3 * i], smem[p + 3 * i + 1], smem[p + 3 * i + 2], smem + sh + 9);
+        filter_params(sh, W_SF(w), w.lane == 0);
+        gsync<T>();
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void store_walker(const WCtx &w, double *gH, double *gR, int wi)
+{
+    double *r = gR + (size_t)wi * w.N * 3;
+    const int p = W_P(w), sh = W_SH(w);
+    for (int i = w.lane; i < 3 * w.N; i += T) r[i] = smem[p + i];
+    if (w.lane < 9) gH[(size_t)wi * 9 + w.lane] = smem[sh + w.lane];
+}
+
+// ---------------------------------------------------------------------------------------------
+// MC_run (MCNS.py:276-392) for a batch of walkers; REPLAY = proposals come from memory.
+// Moves are processed in batches of T: first every lane produces the proposal of ONE move of the
+// batch (Philox and the transcendental part of a proposal run once per move instead of once per
+// lane), then the batch is applied move by move by the whole group.
+// ---------------------------------------------------------------------------------------------
+struct WalkArgs {
+    hans_cfg cfg;
+    double *H, *R;
+    unsigned long long *ctr;
+    const int32_t *ids;
+    int n_active, nmoves;
+    const double *d_limit;
+    double limit;
+    unsigned long long seed;
+    uint32_t gid_base;
+    unsigned long long *attempted, *accepted;
+    double *vol;
+    unsigned long long *pair_tests;
+    const hans_proposal *props; // replay
+    hans_decision *out;
+    int mode;
+};
+
+template <int T, bool REPLAY>
+__global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a)
+{
+    constexpr int GPC = cta_threads<T>() / T;
+    const WCtx w = setup_ctx<T>(a.cfg);
+    const int g = threadIdx.x / T;
+    const double limit = a.d_limit ? *a.d_limit : a.limit;
+    const int mode = a.mode;
+    for (int k0 = blockIdx.x * GPC; k0 < a.n_active; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < a.n_active) {
+            const int wi = a.ids ? a.ids[k] : k;
+            load_walker<T>(w, a.H, a.R, wi, true);
+            const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
+            unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0}; // this lane's share
+            unsigned pairs = 0;
+            unsigned long long pairs_total = 0;
+            PropRec *ring = W_RING(w);
+            for (int m0 = 0; m0 < a.nmoves; m0 += T) {
+                const int nbatch = a.nmoves - m0 < T ? a.nmoves - m0 : T;
+                int my_type = -1;
+                if (w.lane < nbatch) {
+                    PropRec *slot = ring + w.lane;
+                    if (REPLAY) {
+                        const uint4 *q = reinterpret_cast<const uint4 *>(a.props + (size_t)k * a.nmoves + m0 + w.lane);
+                        uint4 *d = reinterpret_cast<uint4 *>(slot);
+                        d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = q[3];
+                        my_type = slot->type;
+                    } else {
+                        const Prop pr = gen_proposal(W_CFG(w), a.seed, a.gid_base + (uint32_t)wi,
+                                                     ctr0 + (unsigned long long)(m0 + w.lane));
+                        slot->type = pr.type; slot->ichain = pr.ichain; slot->idx0 = pr.idx0; slot->idx1 = pr.idx1;
+                        slot->p[0] = pr.p[0]; slot->p[1] = pr.p[1]; slot->p[2] = pr.p[2]; slot->p[3] = pr.p[3];
+                        slot->u_acc = pr.u_acc;
+                        my_type = pr.type;
+                    }
+                }
+                gsync<T>();
+                int my_acc = 0, my_reason = 0;
+                double my_boltz = 0.0;
+                for (int q = 0; q < nbatch; ++q) {
+                    const int type = ring[q].type;
+                    int accepted, reason;
+                    double boltz;
+                    if (type >= HANS_TRANS && type <= HANS_DIH) {
+                        const Dec d = move_chain<T>(w, ring + q, mode, pairs);
+                        accepted = d.accepted; reason = d.reason; boltz = d.boltz;
+                    } else {
+                        const DecP d = move_box<T>(w, q, limit, mode);
+                        accepted = d.accepted; reason = d.reason; boltz = d.boltz; pairs += d.pairs;
+                    }
+                    if (w.lane == q) { my_acc = accepted; my_reason = reason; my_boltz = boltz; }
+                }
+                pairs_total += pairs;
+                pairs = 0;
+                if (my_type >= 0) {
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) { att[t] += (my_type == t); acc[t] += (my_type == t && my_acc); }
+                    if (REPLAY) {
+                        hans_decision *o = a.out + (size_t)k * a.nmoves + m0 + w.lane;
+                        o->accepted = my_acc; o->reason = my_reason; o->boltz = my_boltz;
+                    }
+                }
+                gsync<T>(); // the ring is rewritten by the next batch
+            }
+            store_walker<T>(w, a.H, a.R, wi);
+            if (a.attempted) { // reduce the per-lane counters over the group
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        att[t] += __shfl_down_sync(FULL, att[t], o);
+                        acc[t] += __shfl_down_sync(FULL, acc[t], o);
+                    }
+                    if ((threadIdx.x & 31) == 0) {
+                        atomicAdd(a.attempted + (size_t)k * 6 + t, (unsigned long long)att[t]);
+                        atomicAdd(a.accepted + (size_t)k * 6 + t, (unsigned long long)acc[t]);
+                    }
+                }
+            }
+            if (w.lane == 0) {
+                if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
+                if (a.vol) a.vol[wi] = fabs(det3(smem + W_SH(w)));
+            }
+            if (a.pair_tests) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) pairs_total += __shfl_down_sync(FULL, pairs_total, o);
+                if ((threadIdx.x & 31) == 0 && pairs_total) atomicAdd(a.pair_tests, pairs_total);
+            }
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// float64-only helpers for the non-hot kernels (predicate, change_box, growth)
+// ---------------------------------------------------------------------------------------------
+// all pairs of the beads at `pos` under (H, Hi); same enumeration as trial_overlap
+template <int T>
+__device__ __forceinline__ bool all_overlap64(const WCtx &w, int pos, const double *H, const double *Hi, bool with_intra)
+{
+    const int nb = w.nb, N = w.N, half = N >> 1;
+    const bool even = (N & 1) == 0;
+    const int RB = T < N ? T : N;
+    const int DG = T < N ? 1 : T / N;
+    const int li = w.lane % RB, dg = w.lane / RB;
+    const bool lane_on = dg < DG;
+    bool ov = false;
+    constexpr int U = 4;
+    for (int i0 = 0; i0 < N; i0 += RB) {
+        const int i = i0 + li;
+        const bool row_on = lane_on && i < N;
+        const int ii = row_on ? i : 0;
+        const double xi = smem[pos + 3 * ii], yi = smem[pos + 3 * ii + 1], zi = smem[pos + 3 * ii + 2];
+        const int c0 = (ii / nb) * nb, c1 = c0 + nb;
+        for (int d0 = 1; d0 <= half; d0 += DG * U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int d = d0 + u * DG + dg;
+                if (row_on && d <= half && !(even && d == half && i >= half)) {
+                    int j = i + d;
+                    if (j >= N) j -= N;
+                    const bool same = (j >= c0) && (j < c1);
+                    const int sep = j > i ? j - i : i - j;
+                    if (!same || (with_intra && sep > w.nex))
+                        ov |= (pair_r2(H, Hi, smem[pos + 3 * j] - xi, smem[pos + 3 * j + 1] - yi, smem[pos + 3 * j + 2] - zi) < 1.0);
+                }
+            }
+            if (gany<T>(ov)) return true;
+        }
+    }
+    return false;
+}
+
+// alk.alkane_check_chain_overlap (MCNS.py:198,247,543) for a batch of walkers
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+overlap_kernel(const hans_cfg cfg, const double *gH, const double *gR, const int32_t *ids, int n, int inter_only,
+               int32_t *out)
+{
+    constexpr int GPC = cta_threads<T>() / T;
+    const WCtx w = setup_ctx<T>(cfg);
+    const int g = threadIdx.x / T;
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            load_walker<T>(w, gH, gR, wi, false);
+            double H[9], Hi[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { H[q] = smem[W_SH(w) + q]; Hi[q] = smem[W_SH(w) + 9 + q]; }
+            const bool ov = all_overlap64<T>(w, W_P(w), H, Hi, !inter_only);
+            if (w.lane == 0) out[k] = ov ? 1 : 0;
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// alk.alkane_change_box(ibox, dH) (MCNS.py:186,238,368) for a batch of walkers
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+change_box_kernel(const hans_cfg cfg, double *gH, double *gR, const int32_t *ids, int n, const double *gdH)
+{
+    constexpr int GPC = cta_threads<T>() / T;
+    const WCtx w = setup_ctx<T>(cfg);
+    const int g = threadIdx.x / T;
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            load_walker<T>(w, gH, gR, wi, false);
+            const int sh = W_SH(w);
+            double Hn[9], Hin[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Hn[q] = smem[sh + q] + gdH[(size_t)k * 9 + q];
+            hinv(Hn, Hin);
+            follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), smem + sh + 9, Hn, Hin);
+            if (w.lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) { smem[sh + 18 + q] = Hn[q]; smem[sh + 27 + q] = Hin[q]; }
+            }
+            gsync<T>();
+            commit_trial<T>(w);
+            store_walker<T>(w, gH, gR, wi);
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+// create_initial_configs / populate_boxes (MCNS.py:628-644); alk.alkane_grow_chain (MCNS.py:642).
+// Random insertion with fixed bond length / angle and uniform dihedrals; a chain is retried with
+// the next attempt counter until it overlaps nothing already placed.
+template <int T>
+__global__ void __launch_bounds__(cta_threads<T>())
+grow_kernel(const hans_cfg cfg, const double *gH, double *gR, const int32_t *ids, int n, unsigned long long seed,
+            uint32_t gid_base, int chain_begin, int chain_end, uint32_t attempt_begin, int max_attempts, int32_t *status)
+{
+    constexpr int GPC = cta_threads<T>() / T;
+    const WCtx w = setup_ctx<T>(cfg);
+    const int g = threadIdx.x / T;
+    const int nb = w.nb, P = W_P(w), cn = W_CN(w);
+    for (int k0 = blockIdx.x * GPC; k0 < n; k0 += gridDim.x * GPC) {
+        const int k = k0 + g;
+        if (k < n) {
+            const int wi = ids ? ids[k] : k;
+            const uint32_t gid = gid_base + (uint32_t)wi;
+            load_walker<T>(w, gH, gR, wi, false);
+            double H[9], Hi[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { H[q] = smem[W_SH(w) + q]; Hi[q] = smem[W_SH(w) + 9 + q]; }
+            const int cend = chain_end < 0 ? w.nc : chain_end;
+            int total = 0;
+            bool failed = false;
+            for (int ic = chain_begin; ic < cend && !failed; ++ic) {
+                bool placed = false;
+                for (int at = 0; at < max_attempts && !placed; ++at) {
+                    ++total;
+                    const uint32_t attempt = attempt_begin + (uint32_t)at;
+                    // every lane builds the same trial chain; uniforms u[0..nb+2]
+                    double ua, ub, uc, ud, ue, uf;
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 0u, STREAM_GROW, ua, ub);
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 1u, STREAM_GROW, uc, ud);
+                    draw_block(seed, attempt, (uint32_t)ic, gid, 2u, STREAM_GROW, ue, uf);
+                    double x0, y0, z0;
+                    vecmat(ua, ub, uc, H, x0, y0, z0);
+                    double pp[3] = {x0, y0, z0}, pc[3] = {x0, y0, z0}; // previous-previous, previous
+                    if (w.lane == 0) { smem[cn] = x0; smem[cn + 1] = y0; smem[cn + 2] = z0; }
+                    if (nb > 1) {
+                        const double z = 2.0 * ud - 1.0;
+                        const double st2 = 1.0 - z * z;
+                        const double st = sqrt(st2 > 0.0 ? st2 : 0.0);
+                        double s, co;
+                        hd_sincos(HD_TWO_PI * ue, &s, &co);
+                        pc[0] = x0 + cfg.bondlength * (st * co);
+                        pc[1] = y0 + cfg.bondlength * (st * s);
+                        pc[2] = z0 + cfg.bondlength * z;
+                        if (w.lane == 0) { smem[cn + 3] = pc[0]; smem[cn + 4] = pc[1]; smem[cn + 5] = pc[2]; }
+                    }
+                    double ucur_a = ue, ucur_b = uf; // block 2 holds u[4], u[5]
+                    uint32_t cur_blk = 2u;
+                    for (int kb = 2; kb < nb; ++kb) {
+                        const int ui = 5 + (kb - 2); // index of the uniform for this bead
+                        const uint32_t blk = (uint32_t)(ui >> 1);
+                        if (blk != cur_blk) { draw_block(seed, attempt, (uint32_t)ic, gid, blk, STREAM_GROW, ucur_a, ucur_b); cur_blk = blk; }
+                        const double u = (ui & 1) ? ucur_b : ucur_a;
+                        const double b[3] = {pc[0] - pp[0], pc[1] - pp[1], pc[2] - pp[2]};
+                        const double bn = sqrt(dot3(b, b));
+                        const double uh[3] = {b[0] / bn, b[1] / bn, b[2] / bn};
+                        int ax = 0;
+                        if (fabs(uh[1]) < fabs(uh[ax])) ax = 1;
+                        if (fabs(uh[2]) < fabs(uh[ax])) ax = 2;
+                        double e[3] = {0.0, 0.0, 0.0}, e1[3], e2[3];
+                        e[ax] = 1.0;
+                        cross3(uh, e, e1);
+                        const double n1 = sqrt(dot3(e1, e1));
+                        e1[0] /= n1; e1[1] /= n1; e1[2] /= n1;
+                        cross3(uh, e1, e2);
+                        double s, co;
+                        hd_sincos(HD_TWO_PI * u, &s, &co);
+                        double nw[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const double nd = -cfg.cos_bondangle * uh[q] + cfg.sin_bondangle * (co * e1[q] + s * e2[q]);
+                            nw[q] = pc[q] + cfg.bondlength * nd;
+                        }
+                        if (w.lane == 0) { smem[cn + 3 * kb] = nw[0]; smem[cn + 3 * kb + 1] = nw[1]; smem[cn + 3 * kb + 2] = nw[2]; }
+                        pp[0] = pc[0]; pp[1] = pc[1]; pp[2] = pc[2];
+                        pc[0] = nw[0]; pc[1] = nw[1]; pc[2] = nw[2];
+                    }
+                    gsync<T>();
+                    // against everything already placed (chains < ic), then intra-chain
+                    bool ov = false;
+                    const int M = ic * nb;
+                    for (int base = 0; base < M; base += T) {
+                        const int j = base + w.lane;
+                        if (j < M) {
+                            const double xj = smem[P + 3 * j], yj = smem[P + 3 * j + 1], zj = smem[P + 3 * j + 2];
+                            for (int b = 0; b < nb; ++b)
+                                ov |= (pair_r2(H, Hi, xj - smem[cn + 3 * b], yj - smem[cn + 3 * b + 1], zj - smem[cn + 3 * b + 2]) < 1.0);
+                        }
+                        if (gany<T>(ov)) break;
+                    }
+                    ov = gany<T>(ov);
+                    if (!ov) {
+                        const uchar2 *tab = W_ITAB(w);
+                        for (int e = w.lane; e < w.npc; e += T) {
+                            const uchar2 jb = tab[e];
+                            ov |= pair_r2(H, Hi, smem[cn + 3 * jb.y] - smem[cn + 3 * jb.x], smem[cn + 3 * jb.y + 1] - smem[cn + 3 * jb.x + 1],
+                                          smem[cn + 3 * jb.y + 2] - smem[cn + 3 * jb.x + 2]) < 1.0;
+                        }
+                        ov = gany<T>(ov);
+                    }
+                    if (!ov) {
+                        for (int i = w.lane; i < 3 * nb; i += T) smem[P + 3 * ic * nb + i] = smem[cn + i];
+                        placed = true;
+                    }
+                    gsync<T>();
+                }
+                if (!placed) failed = true;
+            }
+            store_walker<T>(w, const_cast<double *>(gH), gR, wi);
+            if (w.lane == 0 && status) status[k] = failed ? -1 : total;
+            gsync<T>();
+        }
+        if (T != 32) __syncthreads();
+    }
+}
+
+} // namespace hb
