@@ -59,7 +59,7 @@ EXPORTS = [
     "hans_abi_version", "hans_last_error", "hans_device_count", "hans_walker_smem_bytes",
     "hans_moves_per_sweep", "hans_default_threads_per_walker", "hans_mc_run_batch", "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
-    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ffma_peak",
+    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_diag_counters", "hans_ffma_peak",
 ]
 
 
@@ -113,6 +113,7 @@ def _load():
     L.hans_clone.argtypes = [cp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     L.hans_ns_pack.argtypes = [C.POINTER(NsArgs), vp]
     L.hans_ns_resolve.argtypes = [C.POINTER(NsArgs), vp]
+    L.hans_diag_counters.argtypes = [vp, i32]
     L.hans_ffma_peak.argtypes = [i32, C.POINTER(f64), vp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -129,6 +130,13 @@ lib = _load()
 def check(rc: int) -> None:
     if rc != 0:
         raise HansError(f"libhans_b200 error {rc}: {lib.hans_last_error().decode()}")
+
+
+def diag_counters(reset: bool = False):
+    """(float64 chain re-tests, float64 all-pairs passes) since the last reset."""
+    out = (C.c_uint64 * 4)()
+    check(lib.hans_diag_counters(out, int(reset)))
+    return [int(x) for x in out]
 
 
 def moves_per_sweep(nbeads: int, nchains: int) -> int:

@@ -67,15 +67,16 @@ __device__ __noinline__ void hinv(const double *H, double *Hi)
     const double c01 = H[5] * H[6] - H[3] * H[8];
     const double c02 = H[3] * H[7] - H[4] * H[6];
     const double det = (H[0] * c00 + H[1] * c01) + H[2] * c02;
-    Hi[0] = c00 / det;
-    Hi[3] = c01 / det;
-    Hi[6] = c02 / det;
-    Hi[1] = (H[2] * H[7] - H[1] * H[8]) / det;
-    Hi[4] = (H[0] * H[8] - H[2] * H[6]) / det;
-    Hi[7] = (H[1] * H[6] - H[0] * H[7]) / det;
-    Hi[2] = (H[1] * H[5] - H[2] * H[4]) / det;
-    Hi[5] = (H[2] * H[3] - H[0] * H[5]) / det;
-    Hi[8] = (H[0] * H[4] - H[1] * H[3]) / det;
+    const double rd = 1.0 / det;
+    Hi[0] = c00 * rd;
+    Hi[3] = c01 * rd;
+    Hi[6] = c02 * rd;
+    Hi[1] = (H[2] * H[7] - H[1] * H[8]) * rd;
+    Hi[4] = (H[0] * H[8] - H[2] * H[6]) * rd;
+    Hi[7] = (H[1] * H[6] - H[0] * H[7]) * rd;
+    Hi[2] = (H[1] * H[5] - H[2] * H[4]) * rd;
+    Hi[5] = (H[2] * H[3] - H[0] * H[5]) * rd;
+    Hi[8] = (H[0] * H[4] - H[1] * H[3]) * rd;
 }
 
 // o = v.M (row vector times matrix)
@@ -129,6 +130,39 @@ __device__ __noinline__ double max_abs_cos(const double *H)
         if (c > best) best = c;
     }
     return best;
+}
+
+// The cell-shape rejections of box_shear_step / box_stretch_step (MCNS.py:194-197,243-246) as
+// predicates without cbrt / division / arccos:
+//   min_i w_i / V^(1/3) < L,  w_i = V / |a_j x a_k|   <=>   V^2 < (L max_i |a_j x a_k|)^3
+//   min angle < A   <=>   max (a.b)^2 / ((a.a)(b.b)) > cos^2 A
+__device__ __forceinline__ bool aspect_fails(const double *H, double min_ar)
+{
+    const double vol = fabs(det3(H));
+    double m2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double n[3];
+        cross3(H + 3 * ((i + 1) % 3), H + 3 * ((i + 2) % 3), n);
+        const double nn = dot3(n, n);
+        if (nn > m2) m2 = nn;
+    }
+    const double t = min_ar * sqrt(m2);
+    return (vol * vol) < (t * t) * t;
+}
+
+__device__ __forceinline__ bool angle_fails(const double *H, double cos_min_ang)
+{
+    const double c2 = cos_min_ang * cos_min_ang;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double *a = H + 3 * ((i + 1) % 3);
+        const double *b = H + 3 * ((i + 2) % 3);
+        const double ab = dot3(a, b);
+        bad = bad || (ab * ab > c2 * (dot3(a, a) * dot3(b, b)));
+    }
+    return bad;
 }
 
 // squared minimum-image separation of a Cartesian difference (dx,dy,dz); 30 FP64 operations

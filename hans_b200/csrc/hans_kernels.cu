@@ -521,6 +521,19 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream)
     return HANS_OK;
 }
 
+int hans_diag_counters(uint64_t *out4, int reset)
+{
+    if (!out4) return fail(HANS_EINVAL, "out4 is NULL");
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyFromSymbol(h, g_diag, sizeof h));
+    for (int i = 0; i < 4; ++i) out4[i] = h[i];
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyToSymbol(g_diag, z, sizeof z));
+    }
+    return HANS_OK;
+}
+
 int hans_ffma_peak(int iters, double *tflops, void *stream)
 {
     if (!tflops || iters < 1) return fail(HANS_EINVAL, "bad arguments");

@@ -26,6 +26,9 @@
 namespace hb {
 
 extern __shared__ double smem[];
+
+// diagnostics: [0] float64 re-tests of a trial chain (band hits), [1] float64 all-pairs passes
+__device__ unsigned long long g_diag[4];
 #define SMF (reinterpret_cast<float *>(smem))
 #define SM4 (reinterpret_cast<float4 *>(smem))
 
@@ -143,7 +146,8 @@ __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
 // component (two stored roundings + one subtraction), which moves r^2 by <= 2 |G ds| . |d(ds)|
 // <= 9 Lmax 2^-24 |d|; the nine float32 operations and the rounding of G add <= ~10 * 2^-24 times
 // the sum of |terms| <= (sum_i L_i / w_i)^2 |d|^2 (L_i cell vector lengths, w_i perpendicular widths).
-// eps = 2^-24 (16 Lmax + 16 q^2 + 64) * 1.01 carries a further safety factor.  The filter is
+// eps = 2^-24 (8 (1 + Lmax^2) + 144 (Lmax / wmin)^2 + 64) * 1.01 uses square-root free upper bounds of
+// those terms and carries a further safety factor.  The filter is
 // switched off (every pair is re-tested in float64) when a perpendicular width is <= 2.1, where
 // float32 and float64 could wrap a pair to different images that both lie within reach of sigma.
 // SF layout: g00, g11, g22, 2 g01, 2 g02, 2 g12, lo = 1 - eps, hi = 1 + eps.
@@ -153,16 +157,15 @@ __device__ __noinline__ void filter_params(int sh, int sf, bool writer)
     const double *H = smem + sh, *Hi = smem + sh + 9;
     const double g00 = dot3(H, H), g11 = dot3(H + 3, H + 3), g22 = dot3(H + 6, H + 6);
     const double g01 = dot3(H, H + 3), g02 = dot3(H, H + 6), g12 = dot3(H + 3, H + 6);
-    const double L0 = sqrt(g00), L1 = sqrt(g11), L2 = sqrt(g22);
-    const double b0 = sqrt((Hi[0] * Hi[0] + Hi[3] * Hi[3]) + Hi[6] * Hi[6]);
-    const double b1 = sqrt((Hi[1] * Hi[1] + Hi[4] * Hi[4]) + Hi[7] * Hi[7]);
-    const double b2 = sqrt((Hi[2] * Hi[2] + Hi[5] * Hi[5]) + Hi[8] * Hi[8]);
-    const double Lmax = fmax(L0, fmax(L1, L2));
-    const double bmax = fmax(b0, fmax(b1, b2)); // 1 / smallest perpendicular width
-    const double q = (L0 * b0 + L1 * b1) + L2 * b2;
-    const double eps = 5.9604644775390625e-8 * ((16.0 * Lmax + 16.0 * q * q) + 64.0) * 1.01;
+    const double b0 = (Hi[0] * Hi[0] + Hi[3] * Hi[3]) + Hi[6] * Hi[6]; // 1 / w_0^2
+    const double b1 = (Hi[1] * Hi[1] + Hi[4] * Hi[4]) + Hi[7] * Hi[7];
+    const double b2 = (Hi[2] * Hi[2] + Hi[5] * Hi[5]) + Hi[8] * Hi[8];
+    const double L2 = fmax(g00, fmax(g11, g22));   // Lmax^2
+    const double B2 = fmax(b0, fmax(b1, b2));      // 1 / wmin^2
+    // square-root free upper bounds: Lmax <= (1 + Lmax^2)/2, q = sum L_i/w_i <= 3 Lmax/wmin
+    const double eps = 5.9604644775390625e-8 * ((8.0 * (1.0 + L2) + 144.0 * (L2 * B2)) + 64.0) * 1.01;
     float lo = (float)(1.0 - eps), hi = (float)(1.0 + eps);
-    if (!(bmax * 2.1 < 1.0) || !(eps < 0.05)) { lo = -1.0f; hi = 3.0e38f; } // filter off
+    if (!(B2 * 4.41 < 1.0) || !(eps < 0.05)) { lo = -1.0f; hi = 3.0e38f; } // filter off
     if (writer) {
         float *o = SMF + sf;
         o[0] = (float)g00; o[1] = (float)g11; o[2] = (float)g22;
@@ -218,6 +221,7 @@ __device__ __noinline__ bool recheck_chain_exact(WCtx w, int ichain, int b0, boo
 {
     const int nb = w.nb, c0 = ichain * nb, sh = W_SH(w), cn = W_CN(w), p = W_P(w);
     bool ov = false;
+    if (w.lane == 0) atomicAdd(&g_diag[0], 1ull);
     if (amb_inter) {
         for (int j = w.lane; j < w.N; j += T) {
             if ((unsigned)(j - c0) < (unsigned)nb) continue;
@@ -355,15 +359,14 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
 // ---------------------------------------------------------------------------------------------
 // box moves (cold: out of line, context by value)
 // ---------------------------------------------------------------------------------------------
-// all pairs of the TRIAL beads: bead-level round robin.  Lane owns bead i (registers) and walks
-// the offsets d = 1..N/2 with j = (i + d) mod N, so a warp reads consecutive shared-memory words
-// and every unordered pair is visited once (for even N the antipodal offset is taken by the lower
-// half only).  Same-chain pairs are skipped unless with_intra and further apart than nexclude.
+// all pairs of the beads at `pos` in float64 (the reference arithmetic), bead-level round robin:
+// lane owns bead i and walks the offsets d = 1..N/2 with j = (i + d) mod N, so every unordered pair
+// is visited once (for even N the antipodal offset is taken by the lower half only).  Same-chain
+// pairs are skipped unless with_intra and further apart than nexclude.
 template <int T>
-__device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
+__device__ __forceinline__ bool all_overlap64(const WCtx &w, int pos, const double *H, const double *Hi, bool with_intra)
 {
-    const Filt f = load_filt(W_SF(w) + 8);
-    const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18;
+    const int nb = w.nb, N = w.N, half = N >> 1;
     const bool even = (N & 1) == 0;
     const int RB = T < N ? T : N;
     const int DG = T < N ? 1 : T / N;
@@ -375,7 +378,7 @@ __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, un
         const int i = i0 + li;
         const bool row_on = lane_on && i < N;
         const int ii = row_on ? i : 0;
-        const float4 si = SM4[g4 + ii];
+        const double xi = smem[pos + 3 * ii], yi = smem[pos + 3 * ii + 1], zi = smem[pos + 3 * ii + 2];
         const int c0 = (ii / nb) * nb, c1 = c0 + nb;
         for (int d0 = 1; d0 <= half; d0 += DG * U) {
 #pragma unroll
@@ -386,20 +389,85 @@ __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, un
                     if (j >= N) j -= N;
                     const bool same = (j >= c0) && (j < c1);
                     const int sep = j > i ? j - i : i - j;
-                    if (!same || (with_intra && sep > w.nex)) {
-                        const float4 sj = SM4[g4 + j];
-                        const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
-                        if (r2 < f.lo) ov = true;
-                        else if (!(r2 > f.hi))
-                            ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * j] - smem[tp + 3 * i],
-                                          smem[tp + 3 * j + 1] - smem[tp + 3 * i + 1], smem[tp + 3 * j + 2] - smem[tp + 3 * i + 2]) < 1.0;
-                        pairs += 1;
-                    }
+                    if (!same || (with_intra && sep > w.nex))
+                        ov |= (pair_r2(H, Hi, smem[pos + 3 * j] - xi, smem[pos + 3 * j + 1] - yi, smem[pos + 3 * j + 2] - zi) < 1.0);
                 }
             }
             if (gany<T>(ov)) return true;
         }
     }
+    return false;
+}
+
+// float64 test of the TRIAL beads under the trial cell (cold: band hits, single-chain systems)
+template <int T>
+__device__ __noinline__ bool trial_overlap_exact(WCtx w, bool with_intra)
+{
+    double H[9], Hi[9];
+    if (w.lane == 0) atomicAdd(&g_diag[1], 1ull);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { H[k] = smem[W_SH(w) + 18 + k]; Hi[k] = smem[W_SH(w) + 27 + k]; }
+    return all_overlap64<T>(w, W_TP(w), H, Hi, with_intra);
+}
+
+// all pairs of the TRIAL beads through the float32 filter: same enumeration, branch-free inner
+// loop (8 independent pair tests per lane between votes); pairs inside the band are settled by
+// one float64 pass afterwards, and only if nothing overlapped for certain.
+template <int T>
+__device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
+{
+    if (w.nc == 1) return trial_overlap_exact<T>(w, with_intra);
+    const Filt f = load_filt(W_SF(w) + 8);
+    const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w);
+    const bool even = (N & 1) == 0;
+    const int RB = T < N ? T : N;
+    const int DG = T < N ? 1 : T / N;
+    const int li = w.lane % RB, dg = w.lane / RB;
+    const bool lane_on = dg < DG;
+    const int nex_eff = with_intra ? w.nex : 0x3fffffff; // same-chain pairs are tested iff d > nex_eff
+    const int tp = W_TP(w), sh = W_SH(w) + 18;
+    bool ov = false, overflow = false;
+    constexpr int U = 8;
+    for (int i0 = 0; i0 < N; i0 += RB) {
+        const int i = i0 + li;
+        const bool row_on = lane_on && i < N;
+        const int ii = row_on ? i : 0;
+        const float4 si = SM4[g4 + ii];
+        const int dse = nb - 1 - (ii % nb);                                   // d <= dse: same chain
+        const int dmax = row_on ? half - ((even && ii >= half) ? 1 : 0) : 0;  // offsets this lane owns
+        int namb = 0, aj0 = 0, aj1 = 0; // pairs of this row that fell into the band (first two kept)
+        for (int d0 = 1 + dg; d0 <= half; d0 += DG * U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int d = d0 + u * DG;
+                int j = ii + d;
+                if (j >= N) j -= N;
+                const bool valid = (d <= dmax) && ((d > dse) || (d > nex_eff));
+                const float4 sj = SM4[g4 + (valid ? j : ii)];
+                const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
+                ov |= valid && (r2 < f.lo);
+                const bool amb = valid && !(r2 < f.lo) && !(r2 > f.hi);
+                aj1 = (amb && namb == 1) ? j : aj1;
+                aj0 = (amb && namb == 0) ? j : aj0;
+                namb += amb;
+                pairs += valid;
+            }
+            if (gany<T>(ov)) return true;
+        }
+        // pairs inside the band are settled in float64 right away (rigid chains can keep an
+        // intra-chain pair inside the band for a whole walk, so this path must stay cheap)
+        if (gany<T>(namb > 0)) {
+            if (namb > 0)
+                ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj0] - smem[tp + 3 * ii], smem[tp + 3 * aj0 + 1] - smem[tp + 3 * ii + 1],
+                              smem[tp + 3 * aj0 + 2] - smem[tp + 3 * ii + 2]) < 1.0;
+            if (namb > 1)
+                ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj1] - smem[tp + 3 * ii], smem[tp + 3 * aj1 + 1] - smem[tp + 3 * ii + 1],
+                              smem[tp + 3 * aj1 + 2] - smem[tp + 3 * ii + 2]) < 1.0;
+            overflow |= namb > 2;
+            if (gany<T>(ov)) return true;
+        }
+    }
+    if (gany<T>(overflow)) return trial_overlap_exact<T>(w, with_intra);
     return false;
 }
 
@@ -454,12 +522,19 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         const double vol = fabs(det3(H));
         const double vnew_t = vol + p->p[0];
         if (!(vnew_t > 0.0)) return out;
+        // clearly above the ceiling: rejected before any further arithmetic (MCNS.py:351)
+        if (mode == HANS_MODE_FUSED && (vnew_t - volume_limit) > 1e-9 * fabs(volume_limit)) {
+            out.reason = HANS_REJ_CEILING;
+            return out;
+        }
         const double ratio = vnew_t / vol;
         const double s = hd_cbrt(ratio);
 #pragma unroll
         for (int k = 0; k < 9; ++k) Hn[k] = H[k] * s;
         const double new_volume = fabs(det3(Hn)); // MCNS.py:350
-        boltz_f = hd_exp(-c->pressure * p->p[0] + (double)c->nchains * hd_log(ratio)); // MCNS.py:266
+        // exp(-P dV + nchains ln(V'/V)) (MCNS.py:266) as (V'/V)^nchains exp(-P dV)
+        boltz_f = hd_powi(ratio, c->nchains);
+        if (c->pressure != 0.0) boltz_f = boltz_f * hd_exp(-c->pressure * p->p[0]);
         out.boltz = boltz_f;
         if (mode == HANS_MODE_FUSED) {
             // conjunction of MCNS.py:351 evaluated cheapest-first; the O(N^2) overlap test is last
@@ -512,8 +587,8 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         out.accepted = reason == HANS_ACCEPT; out.reason = reason; out.boltz = reason == HANS_ACCEPT ? boltz_f : 0.0;
         return out;
     }
-    if (min_aspect_ratio(Hn) < c->min_ar) reason = HANS_REJ_ASPECT;               // MCNS.py:194,243
-    else if (max_abs_cos(Hn) > c->cos_min_ang) reason = HANS_REJ_ANGLE;           // MCNS.py:196,245
+    if (aspect_fails(Hn, c->min_ar)) reason = HANS_REJ_ASPECT;                    // MCNS.py:194,243
+    else if (angle_fails(Hn, c->cos_min_ang)) reason = HANS_REJ_ANGLE;            // MCNS.py:196,245
     else if (trial_overlap<T>(w, true, out.pairs)) reason = HANS_REJ_OVERLAP;     // MCNS.py:198,247
     if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
         commit_trial<T>(w);
@@ -692,45 +767,8 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// float64-only helpers for the non-hot kernels (predicate, change_box, growth)
+// the non-hot kernels (predicate, change_box, growth): float64 only
 // ---------------------------------------------------------------------------------------------
-// all pairs of the beads at `pos` under (H, Hi); same enumeration as trial_overlap
-template <int T>
-__device__ __forceinline__ bool all_overlap64(const WCtx &w, int pos, const double *H, const double *Hi, bool with_intra)
-{
-    const int nb = w.nb, N = w.N, half = N >> 1;
-    const bool even = (N & 1) == 0;
-    const int RB = T < N ? T : N;
-    const int DG = T < N ? 1 : T / N;
-    const int li = w.lane % RB, dg = w.lane / RB;
-    const bool lane_on = dg < DG;
-    bool ov = false;
-    constexpr int U = 4;
-    for (int i0 = 0; i0 < N; i0 += RB) {
-        const int i = i0 + li;
-        const bool row_on = lane_on && i < N;
-        const int ii = row_on ? i : 0;
-        const double xi = smem[pos + 3 * ii], yi = smem[pos + 3 * ii + 1], zi = smem[pos + 3 * ii + 2];
-        const int c0 = (ii / nb) * nb, c1 = c0 + nb;
-        for (int d0 = 1; d0 <= half; d0 += DG * U) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int d = d0 + u * DG + dg;
-                if (row_on && d <= half && !(even && d == half && i >= half)) {
-                    int j = i + d;
-                    if (j >= N) j -= N;
-                    const bool same = (j >= c0) && (j < c1);
-                    const int sep = j > i ? j - i : i - j;
-                    if (!same || (with_intra && sep > w.nex))
-                        ov |= (pair_r2(H, Hi, smem[pos + 3 * j] - xi, smem[pos + 3 * j + 1] - yi, smem[pos + 3 * j + 2] - zi) < 1.0);
-                }
-            }
-            if (gany<T>(ov)) return true;
-        }
-    }
-    return false;
-}
-
 // alk.alkane_check_chain_overlap (MCNS.py:198,247,543) for a batch of walkers
 template <int T>
 __global__ void __launch_bounds__(cta_threads<T>())

@@ -217,6 +217,10 @@ int hans_ns_pack(const hans_ns_args *a, void *stream);
  * walker list (mpihans.py:236-239), iteration counter += 1 */
 int hans_ns_resolve(const hans_ns_args *a, void *stream);
 
+/* Diagnostics (synchronises): out4[0] = trial chains re-tested in float64 because a pair fell into
+ * the float32 filter's band, out4[1] = float64 all-pairs passes of box moves; reset != 0 zeroes them. */
+int hans_diag_counters(uint64_t *out4, int reset);
+
 /* FP32 FFMA issue-rate probe used as the roofline denominator in bench.py: runs `iters`
  * dependent-chain-free FFMAs per thread on the whole chip, returns achieved TFLOP/s. */
 int hans_ffma_peak(int iters, double *tflops, void *stream);

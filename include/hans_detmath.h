@@ -194,14 +194,32 @@ HANS_HD_BIG void hd_sincos(double x, double *sn, double *cs)
     }
 }
 
-/* cbrt(x) for x > 0: exp(log(x)/3) polished by two Newton steps. */
+/* cbrt(x) for finite x > 0: bit-trick initial guess (a few percent), then Halley iterations
+ * y <- y (y^3 + 2x) / (2 y^3 + x) (cubic convergence) and one Newton polish. */
 HANS_HD_BIG double hd_cbrt(double x)
 {
     if (!(x > 0.0)) return (x == 0.0) ? 0.0 : -hd_from_bits(0x7ff8000000000000ull);
-    double y = hd_exp(hd_log(x) / 3.0);
-    y = y - (y * y * y - x) / (3.0 * y * y);
-    y = y - (y * y * y - x) / (3.0 * y * y);
-    return y;
+    double scale = 1.0;
+    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; scale = 3.814697265625e-06; } /* 2^54, 2^-18 */
+    double y = hd_from_bits(hd_bits(x) / 3ull + 0x2A9F7893782DA1CEull);
+    for (int it = 0; it < 3; ++it) {
+        double y3 = (y * y) * y;
+        y = y * ((y3 + 2.0 * x) / (2.0 * y3 + x));
+    }
+    y = y - ((y * y) * y - x) / (3.0 * (y * y));
+    return y * scale;
+}
+
+/* x^n for an integer n >= 0 by binary exponentiation (fixed multiplication order) */
+HANS_HD double hd_powi(double x, int n)
+{
+    double r = 1.0, b = x;
+    while (n > 0) {
+        if (n & 1) r = r * b;
+        n >>= 1;
+        if (n) b = b * b;
+    }
+    return r;
 }
 
 /* 53-bit uniform in [0,1) from two 32-bit words (hi supplies the top bits). */

@@ -76,15 +76,16 @@ void ho_hinv(const double *H, double *Hi)
     double c01 = H[5] * H[6] - H[3] * H[8];
     double c02 = H[3] * H[7] - H[4] * H[6];
     double det = (H[0] * c00 + H[1] * c01) + H[2] * c02;
-    Hi[0] = c00 / det;
-    Hi[3] = c01 / det;
-    Hi[6] = c02 / det;
-    Hi[1] = (H[2] * H[7] - H[1] * H[8]) / det;
-    Hi[4] = (H[0] * H[8] - H[2] * H[6]) / det;
-    Hi[7] = (H[1] * H[6] - H[0] * H[7]) / det;
-    Hi[2] = (H[1] * H[5] - H[2] * H[4]) / det;
-    Hi[5] = (H[2] * H[3] - H[0] * H[5]) / det;
-    Hi[8] = (H[0] * H[4] - H[1] * H[3]) / det;
+    double rd = 1.0 / det;
+    Hi[0] = c00 * rd;
+    Hi[3] = c01 * rd;
+    Hi[6] = c02 * rd;
+    Hi[1] = (H[2] * H[7] - H[1] * H[8]) * rd;
+    Hi[4] = (H[0] * H[8] - H[2] * H[6]) * rd;
+    Hi[7] = (H[1] * H[6] - H[0] * H[7]) * rd;
+    Hi[2] = (H[1] * H[5] - H[2] * H[4]) * rd;
+    Hi[5] = (H[2] * H[3] - H[0] * H[5]) * rd;
+    Hi[8] = (H[0] * H[4] - H[1] * H[3]) * rd;
 }
 
 /* alk.box_compute_volume (MCNS.py:105,350,392; mpihans.py:183) */
@@ -141,6 +142,38 @@ double ho_max_abs_cos(const double *H)
         if (c > best) best = c;
     }
     return best;
+}
+
+/* The two cell-shape rejections of box_shear_step / box_stretch_step (MCNS.py:194-197,243-246)
+ * as PREDICATES, free of cbrt / division / arccos:
+ *   min_i w_i / V^(1/3) < L  with  w_i = V / |a_j x a_k|   <=>   V^2 < (L max_i |a_j x a_k|)^3
+ *   min angle < A  <=>  max (a.b)^2 / ((a.a)(b.b)) > cos^2 A
+ * (alk.box_min_aspect_ratio is the hs_alkane fork's native routine: its last-bit arithmetic is
+ * unpinned anyway; ho_min_aspect_ratio / ho_max_abs_cos above return the values.) */
+int ho_aspect_fails(const double *H, double min_ar)
+{
+    double vol = ho_volume(H);
+    double m2 = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        double n[3];
+        cross3(H + 3 * ((i + 1) % 3), H + 3 * ((i + 2) % 3), n);
+        double nn = dot3(n, n);
+        if (nn > m2) m2 = nn;
+    }
+    double t = min_ar * sqrt(m2);
+    return (vol * vol) < (t * t) * t;
+}
+
+int ho_angle_fails(const double *H, double cos_min_ang)
+{
+    double c2 = cos_min_ang * cos_min_ang;
+    for (int i = 0; i < 3; ++i) {
+        const double *a = H + 3 * ((i + 1) % 3);
+        const double *b = H + 3 * ((i + 2) % 3);
+        double ab = dot3(a, b);
+        if (ab * ab > c2 * (dot3(a, a) * dot3(b, b))) return 1;
+    }
+    return 0;
 }
 
 /* squared minimum-image separation [A1]: fractional difference through H^-1, subtract the
@@ -476,13 +509,21 @@ static void move_volume(const ho_cfg *c, double *H, double *R, const ho_proposal
     double vol = ho_volume(H);
     double vnew_t = vol + p->p[0];
     if (!(vnew_t > 0.0)) { set_dec(out, 0, HO_REJ_INVALID, 0.0); return; }
+    /* a proposal clearly above the ceiling is rejected before any further arithmetic: the
+     * recomputed volume |det(sH)| differs from V + dV by a few ulp only (MCNS.py:351) */
+    if (mode == HO_MODE_FUSED && (vnew_t - volume_limit) > 1e-9 * fabs(volume_limit)) {
+        set_dec(out, 0, HO_REJ_CEILING, 0.0);
+        return;
+    }
     double ratio = vnew_t / vol;
     double s = hd_cbrt(ratio);
     double Hn[9], Hi[9];
     for (int k = 0; k < 9; ++k) Hn[k] = H[k] * s;
     double new_volume = ho_volume(Hn); /* MCNS.py:350 recomputes it from the cell */
-    /* acceptance weight mirrored at MCNS.py:266 */
-    double boltz_f = hd_exp(-c->pressure * p->p[0] + (double)c->nchains * hd_log(ratio));
+    /* acceptance weight exp(-P dV + nchains ln(V'/V)) (mirrored at MCNS.py:266), evaluated as
+     * (V'/V)^nchains * exp(-P dV); the exponential is skipped for P = 0 (always, from mpihans.py) */
+    double boltz_f = hd_powi(ratio, c->nchains);
+    if (c->pressure != 0.0) boltz_f = boltz_f * hd_exp(-c->pressure * p->p[0]);
 
     if (mode == HO_MODE_FUSED) {
         /* The reference evaluates overlap -> u_acc -> ceiling; the conjunction is order
@@ -544,8 +585,8 @@ static void move_shape(const ho_cfg *c, double *H, double *R, const ho_proposal 
     }
     ho_change_box(c, H, R, dH);                         /* MCNS.py:186,238 */
     int reason = HO_ACCEPT;
-    if (ho_min_aspect_ratio(H) < c->min_ar) reason = HO_REJ_ASPECT;         /* MCNS.py:194,243 */
-    else if (ho_max_abs_cos(H) > c->cos_min_ang) reason = HO_REJ_ANGLE;     /* MCNS.py:196,245 */
+    if (ho_aspect_fails(H, c->min_ar)) reason = HO_REJ_ASPECT;              /* MCNS.py:194,243 */
+    else if (ho_angle_fails(H, c->cos_min_ang)) reason = HO_REJ_ANGLE;      /* MCNS.py:196,245 */
     else if (ho_check_overlap(c, H, R)) reason = HO_REJ_OVERLAP;            /* MCNS.py:198,247 */
     double boltz = reason == HO_ACCEPT ? 1.0 : 0.0;
     set_dec(out, reason == HO_ACCEPT, reason, boltz);

@@ -95,6 +95,8 @@ void ho_hinv(const double *H, double *Hi);
 double ho_volume(const double *H);
 double ho_min_aspect_ratio(const double *H);
 double ho_max_abs_cos(const double *H);
+int ho_aspect_fails(const double *H, double min_ar);
+int ho_angle_fails(const double *H, double cos_min_ang);
 double ho_pair_r2(const double *H, const double *Hi, const double *ri, const double *rj);
 double ho_pair_r2_27(const double *H, const double *ri, const double *rj);
 int ho_moves_per_sweep(int nbeads, int nchains);

@@ -98,6 +98,8 @@ def lib():
     L.ho_volume.argtypes = [vp]; L.ho_volume.restype = C.c_double
     L.ho_min_aspect_ratio.argtypes = [vp]; L.ho_min_aspect_ratio.restype = C.c_double
     L.ho_max_abs_cos.argtypes = [vp]; L.ho_max_abs_cos.restype = C.c_double
+    L.ho_aspect_fails.argtypes = [vp, C.c_double]; L.ho_aspect_fails.restype = C.c_int
+    L.ho_angle_fails.argtypes = [vp, C.c_double]; L.ho_angle_fails.restype = C.c_int
     L.ho_pair_r2.argtypes = [vp, vp, vp, vp]; L.ho_pair_r2.restype = C.c_double
     L.ho_pair_r2_27.argtypes = [vp, vp, vp]; L.ho_pair_r2_27.restype = C.c_double
     L.ho_moves_per_sweep.argtypes = [C.c_int, C.c_int]; L.ho_moves_per_sweep.restype = C.c_int
@@ -167,6 +169,16 @@ def min_aspect_ratio(H) -> float:
 def max_abs_cos(H) -> float:
     H = np.ascontiguousarray(H, dtype=np.float64)
     return lib().ho_max_abs_cos(_p(H))
+
+
+def aspect_fails(H, min_ar) -> int:
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    return lib().ho_aspect_fails(_p(H), float(min_ar))
+
+
+def angle_fails(H, cos_min_ang) -> int:
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    return lib().ho_angle_fails(_p(H), float(cos_min_ang))
 
 
 def pair_r2(H, ri, rj) -> float:
