@@ -63,7 +63,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -283,12 +283,13 @@ def run_b200(args):
     ffma_peak = engine.ffma_peak_tflops()
 
     # ---- device-resident timing (value) --------------------------------------------------------
-    ns.run(args.warmup)
-    launches0 = pool.launches
-    pool.pair_tests.zero_()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    ns.run(args.warmup)
+    barrier()
+    launches0 = pool.launches
+    pool.pair_tests.zero_()
     kev = []
     ms = max_over_ranks(timed_region(args.steps, kernel_events=kev))
     clk = clocks.stop() if rank == 0 else {}
