@@ -63,6 +63,8 @@ struct WCtx {
     int ring; // PropRec index (64-byte units from the start of shared memory)
     int itab; // uchar2 index of the intra-chain pair table
     int cfg;  // double index of the CTA's copy of hans_cfg
+    int wc;   // speculative windows (hans_spec.cuh): double index of the W trial chains [W][3nb]
+    int w4;   //                                      float4 index of their shadows [W][nb]
 };
 #define W_P(w) ((w).D0)
 #define W_TP(w) ((w).D0 + 3 * (w).N)
@@ -99,21 +101,30 @@ __host__ __device__ inline size_t cta_extra_bytes(int nb, int nex)
     return b;
 }
 
-template <int T>
-__device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
+// bytes of the trial chains of a speculative window of W moves (multiple of 64)
+__host__ __device__ inline size_t window_smem_bytes(int nb, int W)
 {
-    constexpr int GPC = cta_threads<T>() / T;
+    return (((size_t)W * nb * 40) + 63) & ~(size_t)63;
+}
+
+// GPC walker groups of T threads per CTA; W > 0 adds the window area behind each walker's ring
+template <int T, int GPC>
+__device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W)
+{
     WCtx w;
     w.nb = c.nbeads; w.nc = c.nchains; w.N = c.nbeads * c.nchains; w.nex = c.nexclude;
     w.npc = intra_pairs_per_chain(w.nb, w.nex);
     w.lane = threadIdx.x % T;
     const int g = threadIdx.x / T;
-    const int per = (int)walker_smem_bytes(w.N, w.nb, T);
+    const int core = (int)walker_smem_bytes(w.N, w.nb, T);
+    const int per = core + (int)window_smem_bytes(w.nb, W);
     const int base = per * g;                                           // bytes
     w.D0 = base / 8;
     const int dbytes = ((8 * (6 * w.N + 3 * w.nb + 36)) + 15) & ~15;
     w.Q0 = (base + dbytes) / 16;
-    w.ring = (base + per - 64 * T) / 64;
+    w.ring = (base + core - 64 * T) / 64;
+    w.wc = (base + core) / 8;
+    w.w4 = (base + core + 24 * W * w.nb + 15) / 16;
     const int extra = per * GPC;
     w.cfg = extra / 8;
     w.itab = (extra + (int)((sizeof(hans_cfg) + 15) & ~(size_t)15)) / 2;
@@ -130,6 +141,11 @@ __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
     }
     __syncthreads();
     return w;
+}
+
+template <int T> __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
+{
+    return setup_ctx_g<T, cta_threads<T>() / T>(c, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,17 +302,19 @@ __device__ __forceinline__ bool chain_overlaps(const WCtx &w, int ichain, int b0
     return false;
 }
 
-// translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
-// alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
-template <int T>
-__device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int mode, unsigned &pairs)
+// Trial chain of a translate / rotate / dihedral proposal, built from the CURRENT chain: beads
+// first, first+stride, ... are written to smem[cn + 3b ..] (float64) and SM4[c4 + b] (shadows).
+// Returns false for a malformed dihedral proposal.  One copy of this arithmetic serves both the
+// cooperative path (first = lane, stride = T) and the speculative windows (hans_spec.cuh).
+__device__ __forceinline__ bool make_trial(const WCtx &w, const PropRec *p, int first, int stride, int cn, int c4,
+                                           int &b0, bool &intra)
 {
-    const int nb = w.nb, type = p->type, ichain = p->ichain;
-    const int c0 = ichain * nb, P = W_P(w) + 3 * c0, cn = W_CN(w), c4 = W_C4(w), sh = W_SH(w);
-    int b0 = 0;
-    bool intra = false;
+    const int nb = w.nb, type = p->type;
+    const int P = W_P(w) + 3 * p->ichain * nb, sh = W_SH(w);
+    b0 = 0;
+    intra = false;
     if (type == HANS_TRANS) {
-        for (int b = w.lane; b < nb; b += T) {
+        for (int b = first; b < nb; b += stride) {
             const double x = smem[P + 3 * b] + p->p[0], y = smem[P + 3 * b + 1] + p->p[1], z = smem[P + 3 * b + 2] + p->p[2];
             smem[cn + 3 * b] = x; smem[cn + 3 * b + 1] = y; smem[cn + 3 * b + 2] = z;
             SM4[c4 + b] = shadow_of(x, y, z, smem + sh + 9);
@@ -306,7 +324,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
         for (int b = 0; b < nb; ++b) { com[0] += smem[P + 3 * b]; com[1] += smem[P + 3 * b + 1]; com[2] += smem[P + 3 * b + 2]; }
         const double dn = (double)nb;
         com[0] /= dn; com[1] /= dn; com[2] /= dn;
-        for (int b = w.lane; b < nb; b += T) {
+        for (int b = first; b < nb; b += stride) {
             const double v[3] = {smem[P + 3 * b] - com[0], smem[P + 3 * b + 1] - com[1], smem[P + 3 * b + 2] - com[2]};
             double o[3];
             quat_rot(p->p, v, o);
@@ -316,7 +334,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
         }
     } else {
         const int ia = p->idx0;
-        if (nb < 4 || ia < 3 || ia > nb - 1) return mkdec(0, HANS_REJ_INVALID, 0.0);
+        if (nb < 4 || ia < 3 || ia > nb - 1) return false;
         const bool flip = p->idx1 != 0;
         const int iv = P + 3 * (flip ? nb - 1 - (ia - 1) : ia - 1);
         const int iw = P + 3 * (flip ? nb - 1 - (ia - 2) : ia - 2);
@@ -327,7 +345,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
         double s, co;
         hd_sincos(0.5 * p->p[0], &s, &co);
         const double q[4] = {co, s * ax[0], s * ax[1], s * ax[2]};
-        for (int b = w.lane; b < nb; b += T) {
+        for (int b = first; b < nb; b += stride) {
             const int src = P + 3 * (flip ? nb - 1 - b : b);
             double r[3] = {smem[src], smem[src + 1], smem[src + 2]};
             if (b >= ia) {
@@ -342,6 +360,19 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
         b0 = ia;
         intra = true;
     }
+    return true;
+}
+
+// translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
+// alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
+template <int T>
+__device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int mode, unsigned &pairs)
+{
+    const int nb = w.nb, ichain = p->ichain;
+    const int c0 = ichain * nb, P = W_P(w) + 3 * c0, cn = W_CN(w), c4 = W_C4(w);
+    int b0 = 0;
+    bool intra = false;
+    if (!make_trial(w, p, w.lane, T, cn, c4, b0, intra)) return mkdec(0, HANS_REJ_INVALID, 0.0);
     gsync<T>();
     const bool ov = chain_overlaps<T>(w, ichain, b0, intra, pairs);
     const double boltz = ov ? 0.0 : 1.0;
