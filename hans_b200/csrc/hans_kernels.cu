@@ -6,7 +6,6 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo  (see
 // __graft_entry__.build()).  -fmad=false is REQUIRED for bit-exact parity with the CPU checker.
 #include "hans_lean.cuh"
-#include "hans_spec.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -270,34 +269,12 @@ static int grid_for(int n, int T)
 
 static int pick_T(const hans_cfg *c, int T)
 {
-    if (T == 0 || (T >= 1 && T <= 16)) T = hans_default_threads_per_walker(c); // 1..16 only steer the walk kernels
+    if (T == 0 || (T >= 1 && T <= 8)) T = hans_default_threads_per_walker(c); // 1..8 only steer the walk kernels
     if (T != 32 && T != 64 && T != 128 && T != 256) return -1;
     return T;
 }
 
-// lanes per move of the speculative-window walk (hans_spec.cuh) for a request `tpw`, 0 = use the
-// cooperative kernel: tpw in {1,2,4,8,16} asks for it explicitly, tpw = 0 picks it when it applies
-static int pick_L(const hans_cfg *c, int tpw)
-{
-    const int L = tpw;
-    if (L != 1 && L != 2 && L != 4 && L != 8 && L != 16) return 0;
-    if (c->nchains > 64) return 0; // the overlap masks are 64 bits wide
-    const int N = c->nchains * c->nbeads;
-    const size_t smem = walker_smem_bytes(N, c->nbeads, 32) + window_smem_bytes(c->nbeads, 32 / L) +
-                        cta_extra_bytes(c->nbeads, c->nexclude);
-    return smem <= 227 * 1024 ? L : 0;
-}
-
 static int spec_grid(int n) { const int cap = sm_count() * 32; return n < cap ? n : cap; }
-
-#define DISPATCH_L(L, ...)                                  \
-    switch (L) {                                            \
-    case 1: { constexpr int LL = 1; __VA_ARGS__; } break;   \
-    case 2: { constexpr int LL = 2; __VA_ARGS__; } break;   \
-    case 4: { constexpr int LL = 4; __VA_ARGS__; } break;   \
-    case 8: { constexpr int LL = 8; __VA_ARGS__; } break;   \
-    default: { constexpr int LL = 16; __VA_ARGS__; } break; \
-    }
 
 // beads-per-chain counts the lean warp-per-walker kernel (hans_lean.cuh) is instantiated for
 static bool lean_applies(const hans_cfg *c)
@@ -317,33 +294,33 @@ static bool lean_applies(const hans_cfg *c)
     default: { constexpr int NN = 12; __VA_ARGS__; } break;  \
     }
 
-template <bool REPLAY> static int launch_lean(const WalkArgs &a, cudaStream_t st)
+// W = 1: one move at a time; 4 / 8: speculative windows (hans_lean.cuh)
+template <bool REPLAY> static int launch_lean(const WalkArgs &a, int W, cudaStream_t st)
 {
     const hans_cfg *c = &a.cfg;
-    const size_t smem = walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32) + cta_extra_bytes(c->nbeads, c->nexclude);
+    const size_t smem = walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32) + window_smem_bytes(c->nbeads, W > 1 ? W : 0) +
+                        cta_extra_bytes(c->nbeads, c->nexclude);
     int rc = HANS_OK;
-    DISPATCH_NB(c->nbeads, {
-        rc = prep_kernel(walk_lean_kernel<NN, REPLAY>, smem);
-        if (rc) return rc;
-        walk_lean_kernel<NN, REPLAY><<<spec_grid(a.n_active), 32, smem, st>>>(a);
-    });
+#define LEAN_LAUNCH(WW)                                                                   \
+    DISPATCH_NB(c->nbeads, {                                                              \
+        rc = prep_kernel(walk_lean_kernel<NN, WW, REPLAY>, smem);                         \
+        if (rc) return rc;                                                                \
+        walk_lean_kernel<NN, WW, REPLAY><<<spec_grid(a.n_active), 32, smem, st>>>(a);     \
+    })
+    if (W == 1) { LEAN_LAUNCH(1); }
+    else if (W == 4) { LEAN_LAUNCH(4); }
+    else { LEAN_LAUNCH(8); }
+#undef LEAN_LAUNCH
     CK(cudaGetLastError());
     return HANS_OK;
 }
 
-template <bool REPLAY> static int launch_spec(const WalkArgs &a, int L, cudaStream_t st)
+// window size of the lean kernel for a request: 0 = default, 1 / 4 / 8 explicit; -1 = not applicable
+static int pick_W(const hans_cfg *c, int tpw)
 {
-    const hans_cfg *c = &a.cfg;
-    const size_t smem = walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32) + window_smem_bytes(c->nbeads, 32 / L) +
-                        cta_extra_bytes(c->nbeads, c->nexclude);
-    int rc = HANS_OK;
-    DISPATCH_L(L, {
-        rc = prep_kernel(walk_spec_kernel<LL, REPLAY>, smem);
-        if (rc) return rc;
-        walk_spec_kernel<LL, REPLAY><<<spec_grid(a.n_active), 32, smem, st>>>(a);
-    });
-    CK(cudaGetLastError());
-    return HANS_OK;
+    if (tpw >= 32 || !lean_applies(c)) return -1;
+    if (tpw == 0) return hans_default_window(c);
+    return (tpw == 1 || tpw == 4 || tpw == 8) ? tpw : -1;
 }
 
 #define DISPATCH_T(T, ...)                                    \
@@ -389,16 +366,10 @@ int hans_default_threads_per_walker(const hans_cfg *cfg)
     return 256;
 }
 
-int hans_default_lanes_per_move(const hans_cfg *cfg)
+int hans_default_window(const hans_cfg *cfg)
 {
-    if (!cfg || cfg->nchains > 64 || cfg->nchains < 2) return 0;
-    const int N = cfg->nchains * cfg->nbeads;
-    if (N > 128) return 0; // larger walkers: one CTA per walker (cooperative kernel)
-    // as many moves in flight as there are chains to spread them over, at most 32
-    if (cfg->nchains >= 48) return 1;
-    if (cfg->nchains >= 24) return 2;
-    if (cfg->nchains >= 12) return 4;
-    return 8;
+    if (!cfg || !lean_applies(cfg)) return 0;
+    return cfg->nchains >= 4 ? 8 : 1; // windows need several chains to spread the moves over
 }
 
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
@@ -413,7 +384,7 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
     if ((d_attempted == nullptr) != (d_accepted == nullptr)) return fail(HANS_EINVAL, "d_attempted and d_accepted go together");
     if (n_active == 0) return HANS_OK;
     const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 2, 4, 8, 16, 32, 64, 128 or 256");
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
     WalkArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ctr = (unsigned long long *)d_ctr; a.ids = d_ids; a.n_active = n_active;
@@ -422,11 +393,10 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
     a.attempted = (unsigned long long *)d_attempted; a.accepted = (unsigned long long *)d_accepted;
     a.vol = d_vol; a.pair_tests = (unsigned long long *)d_pair_tests; a.mode = HANS_MODE_FUSED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (threads_per_walker == 0 && lean_applies(cfg)) return launch_lean<false>(a, st);
-    if (threads_per_walker >= 1 && threads_per_walker < 32) {
-        const int L = pick_L(cfg, threads_per_walker);
-        if (L) return launch_spec<false>(a, L, st);
-        return fail(HANS_ELIMIT, "speculative windows need nchains <= 64 and a walker that fits shared memory");
+    if (threads_per_walker < 32) {
+        const int W = pick_W(cfg, threads_per_walker);
+        if (W > 0) return launch_lean<false>(a, W, st);
+        if (threads_per_walker != 0) return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
     }
     const size_t smem = cta_smem_bytes(cfg, T);
     DISPATCH_T(T, {
@@ -449,17 +419,16 @@ int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_
     if (n_active < 0 || nmoves < 0) return fail(HANS_EINVAL, "negative count");
     if (n_active == 0 || nmoves == 0) return HANS_OK;
     const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 2, 4, 8, 16, 32, 64, 128 or 256");
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
     WalkArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ids = d_ids; a.n_active = n_active; a.nmoves = nmoves;
     a.limit = volume_limit; a.props = d_props; a.out = d_out; a.mode = mode;
     cudaStream_t st = (cudaStream_t)stream;
-    if (threads_per_walker == 0 && mode == HANS_MODE_FUSED && lean_applies(cfg)) return launch_lean<true>(a, st);
-    if (threads_per_walker >= 1 && threads_per_walker < 32 && mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states
-        const int L = pick_L(cfg, threads_per_walker);
-        if (L) return launch_spec<true>(a, L, st);
-        return fail(HANS_ELIMIT, "speculative windows need nchains <= 64 and a walker that fits shared memory");
+    if (threads_per_walker < 32 && mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
+        const int W = pick_W(cfg, threads_per_walker);
+        if (W > 0) return launch_lean<true>(a, W, st);
+        if (threads_per_walker != 0) return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
     }
     const size_t smem = cta_smem_bytes(cfg, T);
     DISPATCH_T(T, {

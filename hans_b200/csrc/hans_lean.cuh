@@ -148,11 +148,167 @@ __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr
     return overlap ? 0 : 1;
 }
 
-template <int NB, bool REPLAY>
+// ---------------------------------------------------------------------------------------------
+// Speculative windows.  A Markov chain is serial, but a window of consecutive single-chain moves
+// can be EVALUATED together: proposals do not depend on the state except through the chain they
+// move, and a hard-body decision is "does the trial chain overlap any bead of another chain".
+//   phase A  the trial chains of all moves of the window are built from the current state (one
+//            lane per trial bead), then every lane tests the resident beads it owns (lane + 32 r)
+//            against every trial bead of every move: bit (r W + k) of `ovw` = "my bead of pass r
+//            certainly overlaps the trial chain of move k" (`ambw`: a pair inside the filter's band).
+//            These are independent pair tests, several in flight per lane -- the instruction-level
+//            parallelism a single serial move does not have;
+//   phase B  ONE REDUX-OR over the warp gives the blocked moves of the whole window.  Moves are
+//            settled in order: blocked moves before the first free one are rejected at no cost;
+//            the free one is accepted and committed, which changes one chain c: the lanes owning
+//            beads of c drop their bits for the later moves (those were against the old
+//            position), the later moves re-test their trial chain against the new chain c only
+//            (a few pairs per lane), and the window is cut before a later move of chain c itself
+//            (its trial was built from the old position; it starts the next window).
+// Every decision is thereby taken against exactly the state the serial order would have produced,
+// so trajectories are bit-identical to the serial kernels and to the CPU checker.
+// Returns the number of moves settled (>= 1); `accbits` = the accepted ones.
+// ---------------------------------------------------------------------------------------------
+template <int W> __device__ __forceinline__ unsigned fold_passes(unsigned x)
+{
+    x |= x >> (2 * W);
+    x |= x >> W;
+    return x & ((1u << W) - 1u);
+}
+
+template <int NB, int W>
+__device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, int q, int nw, unsigned &accbits,
+                                           unsigned &pairs)
+{
+    static_assert(W == 4 || W == 8, "four passes of W bits share one 32-bit word");
+    const PropRec *ring = W_RING(w) + q;
+    const int lane = w.lane, N = w.N, f4 = W_F4(w), np = (N + 31) >> 5;
+    const Filt &f = cr.f;
+
+    // ---- phase A ------------------------------------------------------------------------------
+    for (int e = lane; e < nw * NB; e += 32) { // one lane per trial bead
+        const int k = e / NB, b = e - k * NB;
+        int b0;
+        bool intra;
+        make_trial(w, ring + k, b, NB, w.wc + 3 * NB * k, w.w4 + NB * k, b0, intra);
+    }
+    const int myck = lane < nw ? ring[lane].ichain : -1; // lane k remembers the chain of move k
+    __syncwarp();
+    unsigned ovw = 0, ambw = 0;   // bit r W + k, against the state at the start of the window
+    unsigned fixw = 0, afixw = 0; // bit k: intra-chain pairs, and pairs against chains committed in this window
+    unsigned dih = 0;
+    for (int r0 = 0; r0 < np; r0 += 2) {
+        const int j0 = lane + 32 * r0, j1 = j0 + 32;
+        const bool live0 = j0 < N, live1 = j1 < N;
+        const float4 s0 = SM4[f4 + (live0 ? j0 : 0)], s1 = SM4[f4 + (live1 ? j1 : 0)];
+        const int cj0 = j0 / NB, cj1 = j1 / NB;
+#pragma unroll 2
+        for (int k = 0; k < nw; ++k) {
+            const int4 hd = *reinterpret_cast<const int4 *>(ring + k);
+            const int b0 = hd.x == HANS_DIH ? hd.z : 0;
+            if (hd.x == HANS_DIH) dih |= 1u << k;
+            bool o0 = false, o1 = false, a0 = false, a1 = false;
+#pragma unroll(NB <= 2 ? NB : 1)
+            for (int b = b0; b < NB; ++b) {
+                const float4 t = SM4[w.w4 + NB * k + b];
+                const float ra = r2_f32(f, s0.x - t.x, s0.y - t.y, s0.z - t.z);
+                const float rb = r2_f32(f, s1.x - t.x, s1.y - t.y, s1.z - t.z);
+                o0 |= ra < f.lo; a0 |= !(ra > f.hi);
+                o1 |= rb < f.lo; a1 |= !(rb > f.hi);
+            }
+            const bool on0 = live0 && cj0 != hd.y, on1 = live1 && cj1 != hd.y;
+            ovw |= ((on0 && o0) ? 1u : 0u) << (r0 * W + k) | ((on1 && o1) ? 1u : 0u) << (r0 * W + W + k);
+            ambw |= ((on0 && a0) ? 1u : 0u) << (r0 * W + k) | ((on1 && a1) ? 1u : 0u) << (r0 * W + W + k);
+            pairs += (unsigned)(((on0 ? 1 : 0) + (on1 ? 1 : 0)) * (NB - b0));
+        }
+    }
+    if (NB >= 4 && dih) { // dihedral moves: intra-chain pairs (j, b), b >= b0, beyond the exclusion
+        const uchar2 *tab = W_ITAB(w);
+        for (int k = 0; k < nw; ++k) {
+            if (!((dih >> k) & 1u)) continue;
+            const int b0 = ring[k].idx0, t4 = w.w4 + NB * k;
+            for (int e = lane; e < w.npc; e += 32) {
+                const uchar2 jb = tab[e];
+                if ((int)jb.y >= b0) {
+                    const float4 a = SM4[t4 + jb.x], b = SM4[t4 + jb.y];
+                    const float r2 = r2_f32(f, b.x - a.x, b.y - a.y, b.z - a.z);
+                    if (r2 < f.lo) fixw |= 1u << k;
+                    if (!(r2 > f.hi)) afixw |= 1u << k;
+                    pairs += 1;
+                }
+            }
+        }
+    }
+
+    // ---- phase B ------------------------------------------------------------------------------
+    accbits = 0;
+    unsigned pend = (nw >= 32) ? FULL : ((1u << nw) - 1u);
+    constexpr int LB = 32 / W; // lanes per later move in the fix-ups
+    for (;;) {
+        const unsigned blocked = fold_passes<W>(__reduce_or_sync(FULL, ovw | fixw));
+        const unsigned cand = pend & ~blocked;
+        if (!cand) break; // every move still pending overlaps something: rejected
+        const unsigned band = fold_passes<W>(__reduce_or_sync(FULL, ambw | afixw));
+        const int i = __ffs(cand) - 1;
+        pend &= ~((2u << i) - 1u);
+        const PropRec *pi = ring + i;
+        const int ci = pi->ichain, b0i = pi->type == HANS_DIH ? pi->idx0 : 0;
+        const int wci = w.wc + 3 * NB * i, w4i = w.w4 + NB * i;
+        if ((band >> i) & 1u) { // no certain overlap, but a pair inside the band: float64 decides
+            const int cn = W_CN(w);
+            for (int e = lane; e < 3 * NB; e += 32) smem[cn + e] = smem[wci + e];
+            __syncwarp();
+            if (lean_recheck(w, ci, b0i, true, pi->type == HANS_DIH)) continue;
+        }
+        accbits |= 1u << i;
+        if (!(pi->u_acc < 1.0)) continue; // MCNS.py:372 with boltz = 1 (only explicit proposals can fail it)
+        {
+            const int P = W_P(w) + 3 * NB * ci, f4c = f4 + NB * ci;
+            for (int e = lane; e < 3 * NB; e += 32) smem[P + e] = smem[wci + e];
+            for (int e = lane; e < NB; e += 32) SM4[f4c + e] = SM4[w4i + e];
+        }
+        __syncwarp();
+        if (!pend) break;
+        // a later move of the same chain was built from the old position: it starts the next window
+        const unsigned stale = __ballot_sync(FULL, lane > i && myck == ci) & pend;
+        if (stale) {
+            nw = __ffs(stale) - 1;
+            pend &= (1u << nw) - 1u;
+            if (!pend) break;
+        }
+        // my beads of chain ci were tested at their old position: those bits are void
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((lane + 32 * r) / NB == ci) { ovw &= ~(((1u << W) - 1u) << (r * W)); ambw &= ~(((1u << W) - 1u) << (r * W)); }
+        // the later moves against the new chain ci
+        {
+            const int k = i + 1 + lane / LB, sub = lane % LB;
+            if (k < nw) {
+                const int b0 = ring[k].type == HANS_DIH ? ring[k].idx0 : 0;
+                bool o = false, am = false;
+                for (int bb = sub; bb < NB; bb += LB) {
+                    const float4 sn = SM4[f4 + NB * ci + bb];
+                    for (int b = b0; b < NB; ++b) {
+                        const float4 t = SM4[w.w4 + NB * k + b];
+                        const float r2 = r2_f32(f, sn.x - t.x, sn.y - t.y, sn.z - t.z);
+                        o |= r2 < f.lo; am |= !(r2 > f.hi);
+                    }
+                    pairs += (unsigned)(NB - b0);
+                }
+                if (o) fixw |= 1u << k;
+                if (am) afixw |= 1u << k;
+            }
+        }
+    }
+    return nw;
+}
+
+// W = 1: strictly one move at a time; W = 4 / 8: speculative windows of up to W moves
+template <int NB, int W, bool REPLAY>
 __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
 {
     constexpr int T = 32;
-    const WCtx w = setup_ctx_g<32, 1>(a.cfg, 0);
+    const WCtx w = setup_ctx_g<32, 1>(a.cfg, W > 1 ? W : 0);
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     for (int k = blockIdx.x; k < a.n_active; k += gridDim.x) {
         const int wi = a.ids ? a.ids[k] : k;
@@ -166,6 +322,7 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
         for (int m0 = 0; m0 < a.nmoves; m0 += T) {
             const int nbatch = a.nmoves - m0 < T ? a.nmoves - m0 : T;
             int my_type = -1;
+            bool my_plain = false; // a single-chain move with a well-formed proposal
             if (w.lane < nbatch) {
                 PropRec *slot = ring + w.lane;
                 if (REPLAY) {
@@ -181,11 +338,32 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
                     slot->u_acc = pr.u_acc;
                     my_type = pr.type;
                 }
+                my_plain = (my_type == HANS_TRANS || (NB > 1 && my_type == HANS_ROT) ||
+                            (my_type == HANS_DIH && NB >= 4 && slot->idx0 >= 3 && slot->idx0 <= NB - 1)) &&
+                           (unsigned)slot->ichain < (unsigned)w.nc;
             }
             __syncwarp();
+            const unsigned plain = W > 1 ? __ballot_sync(FULL, my_plain) : 0u;
             int my_acc = 0, my_reason = 0;
             double my_boltz = 0.0;
             for (int q = 0; q < nbatch; ++q) {
+                if (W > 1) { // a run of at least two plain single-chain moves: settle it as a window
+                    const unsigned run = ~(plain >> q);
+                    int nw = run ? __ffs(run) - 1 : 32;
+                    if (nw > W) nw = W;
+                    if (nw >= 2) {
+                        unsigned ab;
+                        const int done = lean_window<NB, (W > 1 ? W : 4)>(w, cr, q, nw, ab, pairs);
+                        const int rel = w.lane - q;
+                        if (rel >= 0 && rel < done) {
+                            my_acc = (int)((ab >> rel) & 1u);
+                            my_reason = my_acc ? HANS_ACCEPT : HANS_REJ_OVERLAP;
+                            my_boltz = my_acc ? 1.0 : 0.0;
+                        }
+                        q += done - 1;
+                        continue;
+                    }
+                }
                 const PropRec *p = ring + q;
                 const int4 hd = *reinterpret_cast<const int4 *>(p); // type, ichain, idx0, idx1
                 const int type = hd.x, ichain = hd.y;

@@ -404,7 +404,7 @@ __device__ __forceinline__ bool all_overlap64(const WCtx &w, int pos, const doub
     const int li = w.lane % RB, dg = w.lane / RB;
     const bool lane_on = dg < DG;
     bool ov = false;
-    constexpr int U = 4;
+    constexpr int U = 1;
     for (int i0 = 0; i0 < N; i0 += RB) {
         const int i = i0 + li;
         const bool row_on = lane_on && i < N;
@@ -458,7 +458,7 @@ __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, un
     const int nex_eff = with_intra ? w.nex : 0x3fffffff; // same-chain pairs are tested iff d > nex_eff
     const int tp = W_TP(w), sh = W_SH(w) + 18;
     bool ov = false, overflow = false;
-    constexpr int U = 8;
+    constexpr int U = 2;
     for (int i0 = 0; i0 < N; i0 += RB) {
         const int i = i0 + li;
         const bool row_on = lane_on && i < N;
@@ -503,20 +503,24 @@ __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, un
 }
 
 // chains follow a cell change rigidly (first bead keeps its fractional coordinates): beads at
-// `src` under Hi_old -> beads at `dst` under H_new, and their float32 shadows under Hi_new
+// `src` under the inverse cell at smem[hi_old] -> beads at `dst` under the cell at smem[h_new], and
+// their float32 shadows under its inverse at smem[hi_new].  Out of line, one copy: a box move applies
+// it once, a rejected shear / stretch twice (instruction-cache footprint, profiles/r01_*).
 template <int T>
-__device__ __forceinline__ void follow_cell(const WCtx &w, int src, int dst, int dst4, const double *Hi_old,
-                                            const double *H_new, const double *Hi_new)
+__device__ __noinline__ void follow_cell(WCtx w, int src, int dst, int dst4, int hi_old, int h_new, int hi_new)
 {
+    double Hio[9], Hn[9], Hin[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Hio[k] = smem[hi_old + k]; Hn[k] = smem[h_new + k]; Hin[k] = smem[hi_new + k]; }
     for (int i = w.lane; i < w.N; i += T) {
         const int a = src + 3 * ((i / w.nb) * w.nb);
         const double ax = smem[a], ay = smem[a + 1], az = smem[a + 2];
         double f0, f1, f2, n0, n1, n2;
-        vecmat(ax, ay, az, Hi_old, f0, f1, f2);
-        vecmat(f0, f1, f2, H_new, n0, n1, n2);
+        vecmat(ax, ay, az, Hio, f0, f1, f2);
+        vecmat(f0, f1, f2, Hn, n0, n1, n2);
         const double x = smem[src + 3 * i] + (n0 - ax), y = smem[src + 3 * i + 1] + (n1 - ay), z = smem[src + 3 * i + 2] + (n2 - az);
         smem[dst + 3 * i] = x; smem[dst + 3 * i + 1] = y; smem[dst + 3 * i + 2] = z;
-        SM4[dst4 + i] = shadow_of(x, y, z, Hi_new);
+        SM4[dst4 + i] = shadow_of(x, y, z, Hin);
     }
 }
 
@@ -603,43 +607,42 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         for (int k = 0; k < 9; ++k) Hn[k] = H[k] + dH[k];
     }
     hinv(Hn, Hin);
-    follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), smem + sh + 9, Hn, Hin); // alk.alkane_change_box, MCNS.py:186,238
     if (w.lane == 0) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) { smem[sh + 18 + k] = Hn[k]; smem[sh + 27 + k] = Hin[k]; }
     }
     gsync<T>();
+    follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), sh + 9, sh + 18, sh + 27); // alk.alkane_change_box, MCNS.py:186,238
     filter_params(sh + 18, W_SF(w) + 8, w.lane == 0);
     gsync<T>();
     int reason = HANS_ACCEPT;
-    if (is_vol) {
-        if (trial_overlap<T>(w, false, out.pairs)) reason = HANS_REJ_OVERLAP;
-        if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) commit_trial<T>(w);
-        out.accepted = reason == HANS_ACCEPT; out.reason = reason; out.boltz = reason == HANS_ACCEPT ? boltz_f : 0.0;
-        return out;
+    if (!is_vol) {
+        if (aspect_fails(Hn, c->min_ar)) reason = HANS_REJ_ASPECT;                // MCNS.py:194,243
+        else if (angle_fails(Hn, c->cos_min_ang)) reason = HANS_REJ_ANGLE;        // MCNS.py:196,245
     }
-    if (aspect_fails(Hn, c->min_ar)) reason = HANS_REJ_ASPECT;                    // MCNS.py:194,243
-    else if (angle_fails(Hn, c->cos_min_ang)) reason = HANS_REJ_ANGLE;            // MCNS.py:196,245
-    else if (trial_overlap<T>(w, true, out.pairs)) reason = HANS_REJ_OVERLAP;     // MCNS.py:198,247
+    if (reason == HANS_ACCEPT && trial_overlap<T>(w, !is_vol, out.pairs)) reason = HANS_REJ_OVERLAP; // MCNS.py:198,247
     if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
         commit_trial<T>(w);
-    } else {
+    } else if (!is_vol) {
         // MCNS.py:366-368: the reference reverts by applying -dH through alkane_change_box, which
-        // is not an exact restore; reproduce that arithmetic from the trial state.
+        // is not an exact restore; reproduce that arithmetic from the trial state.  (A rejected
+        // volume move needs nothing: the saved cell and chains were never overwritten.)
         double H2[9], H2i[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) H2[k] = Hn[k] + (-1.0 * dH[k]);
         hinv(H2, H2i);
-        follow_cell<T>(w, W_TP(w), W_P(w), W_F4(w), Hin, H2, H2i);
+        gsync<T>(); // every thread has read the old cell
         if (w.lane == 0) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) { smem[sh + k] = H2[k]; smem[sh + 9 + k] = H2i[k]; }
         }
         gsync<T>();
+        follow_cell<T>(w, W_TP(w), W_P(w), W_F4(w), sh + 27, sh, sh + 9);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
     }
-    out.accepted = reason == HANS_ACCEPT; out.reason = reason; out.boltz = reason == HANS_ACCEPT ? 1.0 : 0.0;
+    out.accepted = reason == HANS_ACCEPT; out.reason = reason;
+    out.boltz = reason == HANS_ACCEPT ? (is_vol ? boltz_f : 1.0) : 0.0;
     return out;
 }
 
@@ -843,11 +846,12 @@ change_box_kernel(const hans_cfg cfg, double *gH, double *gR, const int32_t *ids
 #pragma unroll
             for (int q = 0; q < 9; ++q) Hn[q] = smem[sh + q] + gdH[(size_t)k * 9 + q];
             hinv(Hn, Hin);
-            follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), smem + sh + 9, Hn, Hin);
             if (w.lane == 0) {
 #pragma unroll
                 for (int q = 0; q < 9; ++q) { smem[sh + 18 + q] = Hn[q]; smem[sh + 27 + q] = Hin[q]; }
             }
+            gsync<T>();
+            follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), sh + 9, sh + 18, sh + 27);
             gsync<T>();
             commit_trial<T>(w);
             store_walker<T>(w, gH, gR, wi);

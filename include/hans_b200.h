@@ -101,9 +101,9 @@ int64_t hans_walker_smem_bytes(const hans_cfg *cfg);
 int hans_moves_per_sweep(int nbeads, int nchains);
 /* default threads per walker for a shape (32 = one warp per walker, else one CTA per walker) */
 int hans_default_threads_per_walker(const hans_cfg *cfg);
-/* lanes per move of the speculative-window walk kernel chosen for a shape when
- * threads_per_walker = 0 (1, 2, 4, 8 or 16); 0 = the shape runs on the cooperative kernel */
-int hans_default_lanes_per_move(const hans_cfg *cfg);
+/* window size the warp-per-walker kernel uses for a shape when threads_per_walker = 0 (1 = one
+ * move at a time, 4 / 8 = speculative windows); 0 = the shape runs on the cooperative kernel */
+int hans_default_window(const hans_cfg *cfg);
 
 /* ---- the fused hot path ---------------------------------------------------------------------
  * MC_run (NesSa/MCNS.py:276-392) for n_active walkers at once: sweeps * moves_per_sweep trial
@@ -115,10 +115,11 @@ int hans_default_lanes_per_move(const hans_cfg *cfg);
  * d_pair_tests        device scalar, executed pair tests accumulated (may be NULL)
  * threads_per_walker  32, 64, 128, 256: cooperative kernel, the walker's threads share every move
  *                     (32 = one warp per walker, else one CTA per walker);
- *                     1, 2, 4, 8, 16: speculative windows -- one warp per walker, 32/L consecutive
- *                     single-chain moves in flight with L lanes each, settled in order (same
- *                     decisions and trajectory, bit for bit); needs nchains <= 64;
- *                     0 = hans_default_lanes_per_move if it applies, else
+ *                     1, 4, 8: warp-per-walker kernel specialised on nbeads (needs nchains*nbeads
+ *                     <= 128, nbeads in {1,2,4,6,8,12}); 1 = one move at a time, 4 / 8 = speculative
+ *                     windows of that many consecutive single-chain moves, settled in order (same
+ *                     decisions and trajectory, bit for bit);
+ *                     0 = hans_default_window if the shape qualifies, else
  *                     hans_default_threads_per_walker
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
