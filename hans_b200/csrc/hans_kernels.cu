@@ -372,10 +372,56 @@ int hans_default_window(const hans_cfg *cfg)
     return cfg->nchains >= 4 ? 8 : 1; // windows need several chains to spread the moves over
 }
 
-int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
-                      int n_active, int sweeps, const double *d_volume_limit, double volume_limit, uint64_t seed,
-                      uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted, double *d_vol,
-                      uint64_t *d_pair_tests, int threads_per_walker, void *stream)
+static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
+{
+    int rc = HANS_OK;
+    if (threads_per_walker < 32 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
+        const int W = pick_W(cfg, threads_per_walker);
+        if (W > 0) return from_memory ? launch_lean<true>(a, W, st) : launch_lean<false>(a, W, st);
+        if (threads_per_walker != 0)
+            return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
+    }
+    const int T = pick_T(cfg, threads_per_walker);
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
+    const size_t smem = cta_smem_bytes(cfg, T);
+    if (from_memory) {
+        DISPATCH_T(T, {
+            rc = prep_kernel(walk_kernel<TT, true>, smem);
+            if (rc) return rc;
+            walk_kernel<TT, true><<<grid_for(a.n_active, TT), cta_threads<TT>(), smem, st>>>(a);
+        });
+    } else {
+        DISPATCH_T(T, {
+            rc = prep_kernel(walk_kernel<TT, false>, smem);
+            if (rc) return rc;
+            walk_kernel<TT, false><<<grid_for(a.n_active, TT), cta_threads<TT>(), smem, st>>>(a);
+        });
+    }
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_gen_proposals(const hans_cfg *cfg, const uint64_t *d_ctr, const int32_t *d_ids, int n_active, int nmoves,
+                       uint64_t seed, uint32_t gid_base, hans_proposal *d_props, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_ctr || !d_props) return fail(HANS_EINVAL, "d_ctr and d_props are required");
+    if (n_active < 0 || nmoves < 0) return fail(HANS_EINVAL, "negative count");
+    if (n_active == 0 || nmoves == 0) return HANS_OK;
+    const size_t total = (size_t)n_active * (size_t)nmoves;
+    const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 64;
+    gen_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        *cfg, (const unsigned long long *)d_ctr, d_ids, n_active, nmoves, seed, gid_base, d_props);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
+                         int n_active, int sweeps, const double *d_volume_limit, double volume_limit, uint64_t seed,
+                         uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted, double *d_vol,
+                         uint64_t *d_pair_tests, int threads_per_walker, void *d_workspace, uint64_t workspace_bytes,
+                         void *stream)
 {
     int rc = check_cfg(cfg);
     if (rc) return rc;
@@ -383,8 +429,6 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
     if (n_active < 0 || sweeps < 0) return fail(HANS_EINVAL, "negative n_active / sweeps");
     if ((d_attempted == nullptr) != (d_accepted == nullptr)) return fail(HANS_EINVAL, "d_attempted and d_accepted go together");
     if (n_active == 0) return HANS_OK;
-    const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
     WalkArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ctr = (unsigned long long *)d_ctr; a.ids = d_ids; a.n_active = n_active;
@@ -393,19 +437,31 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
     a.attempted = (unsigned long long *)d_attempted; a.accepted = (unsigned long long *)d_accepted;
     a.vol = d_vol; a.pair_tests = (unsigned long long *)d_pair_tests; a.mode = HANS_MODE_FUSED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (threads_per_walker < 32) {
-        const int W = pick_W(cfg, threads_per_walker);
-        if (W > 0) return launch_lean<false>(a, W, st);
-        if (threads_per_walker != 0) return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
-    }
-    const size_t smem = cta_smem_bytes(cfg, T);
-    DISPATCH_T(T, {
-        rc = prep_kernel(walk_kernel<TT, false>, smem);
+    // moves per chunk the workspace holds (a multiple of 32: the kernels take proposals 32 at a time)
+    const uint64_t per_move = (uint64_t)n_active * sizeof(hans_proposal);
+    uint64_t chunk = d_workspace ? (workspace_bytes / per_move) & ~(uint64_t)31 : 0;
+    if (chunk == 0) return launch_walk(cfg, a, false, threads_per_walker, st); // no workspace: generate in the kernel
+    const int total = a.nmoves;
+    for (int m0 = 0; m0 < total; m0 += (int)chunk) {
+        const int n = total - m0 < (int)chunk ? total - m0 : (int)chunk;
+        rc = hans_gen_proposals(cfg, d_ctr, d_ids, n_active, n, seed, gid_base, (hans_proposal *)d_workspace, stream);
         if (rc) return rc;
-        walk_kernel<TT, false><<<grid_for(n_active, TT), cta_threads<TT>(), smem, st>>>(a);
-    });
-    CK(cudaGetLastError());
+        a.nmoves = n;
+        a.props = (const hans_proposal *)d_workspace;
+        a.out = nullptr;
+        rc = launch_walk(cfg, a, true, threads_per_walker, st); // advances d_ctr by n
+        if (rc) return rc;
+    }
     return HANS_OK;
+}
+
+int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
+                      int n_active, int sweeps, const double *d_volume_limit, double volume_limit, uint64_t seed,
+                      uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted, double *d_vol,
+                      uint64_t *d_pair_tests, int threads_per_walker, void *stream)
+{
+    return hans_mc_run_batch_ws(cfg, d_H, d_R, d_ctr, d_ids, n_active, sweeps, d_volume_limit, volume_limit, seed, gid_base,
+                                d_attempted, d_accepted, d_vol, d_pair_tests, threads_per_walker, nullptr, 0, stream);
 }
 
 int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n_active,
@@ -418,26 +474,11 @@ int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_
     if (mode != HANS_MODE_FUSED && mode != HANS_MODE_PROPOSE) return fail(HANS_EINVAL, "bad mode");
     if (n_active < 0 || nmoves < 0) return fail(HANS_EINVAL, "negative count");
     if (n_active == 0 || nmoves == 0) return HANS_OK;
-    const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
     WalkArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ids = d_ids; a.n_active = n_active; a.nmoves = nmoves;
     a.limit = volume_limit; a.props = d_props; a.out = d_out; a.mode = mode;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (threads_per_walker < 32 && mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
-        const int W = pick_W(cfg, threads_per_walker);
-        if (W > 0) return launch_lean<true>(a, W, st);
-        if (threads_per_walker != 0) return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
-    }
-    const size_t smem = cta_smem_bytes(cfg, T);
-    DISPATCH_T(T, {
-        rc = prep_kernel(walk_kernel<TT, true>, smem);
-        if (rc) return rc;
-        walk_kernel<TT, true><<<grid_for(n_active, TT), cta_threads<TT>(), smem, st>>>(a);
-    });
-    CK(cudaGetLastError());
-    return HANS_OK;
+    return launch_walk(cfg, a, true, threads_per_walker, (cudaStream_t)stream);
 }
 
 int hans_check_overlap(const hans_cfg *cfg, const double *d_H, const double *d_R, const int32_t *d_ids, int n,

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
             if (my_type >= 0) {
 #pragma unroll
                 for (int t = 0; t < 6; ++t) { att[t] += (my_type == t); acc[t] += (my_type == t && my_acc); }
-                if (REPLAY) {
+                if (REPLAY && a.out) {
                     hans_decision *o = a.out + (size_t)k * a.nmoves + m0 + w.lane;
                     o->accepted = my_acc; o->reason = my_reason; o->boltz = my_boltz;
                 }
@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
         }
         if (w.lane == 0) {
             if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
+            else if (a.ctr) a.ctr[wi] += (unsigned long long)a.nmoves; // proposals came from hans_gen_proposals
             if (a.vol) a.vol[wi] = fabs(det3(smem + W_SH(w)));
         }
         if (a.pair_tests) {

@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
                 if (my_type >= 0) {
 #pragma unroll
                     for (int t = 0; t < 6; ++t) { att[t] += (my_type == t); acc[t] += (my_type == t && my_acc); }
-                    if (REPLAY) {
+                    if (REPLAY && a.out) {
                         hans_decision *o = a.out + (size_t)k * a.nmoves + m0 + w.lane;
                         o->accepted = my_acc; o->reason = my_reason; o->boltz = my_boltz;
                     }
@@ -787,6 +787,7 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
             }
             if (w.lane == 0) {
                 if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
+                else if (a.ctr) a.ctr[wi] += (unsigned long long)a.nmoves; // proposals came from hans_gen_proposals
                 if (a.vol) a.vol[wi] = fabs(det3(smem + W_SH(w)));
             }
             if (a.pair_tests) {
@@ -797,6 +798,32 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
             gsync<T>();
         }
         if (T != 32) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Proposals of a walk, generated ahead of it: one thread per (walker, move).  Proposals do not depend
+// on the state, so this throughput-bound part (Philox, Box-Muller, quaternions) runs at full
+// occupancy here instead of on the latency-bound critical path -- and outside the instruction-cache
+// footprint -- of the walk kernels, which then read 64 bytes per move from HBM.
+// props[k][m] = proposal number ctr[walker k] + m of walker k (same stream as the fused kernels).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gen_kernel(const hans_cfg cfg, const unsigned long long *ctr, const int32_t *ids,
+                                                  int n_active, int nmoves, unsigned long long seed, uint32_t gid_base,
+                                                  hans_proposal *props)
+{
+    const size_t total = (size_t)n_active * (size_t)nmoves;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t / (size_t)nmoves), m = (int)(t - (size_t)k * nmoves);
+        const int wi = ids ? ids[k] : k;
+        const Prop pr = gen_proposal(&cfg, seed, gid_base + (uint32_t)wi, ctr[wi] + (unsigned long long)m);
+        PropRec r;
+        r.type = pr.type; r.ichain = pr.ichain; r.idx0 = pr.idx0; r.idx1 = pr.idx1;
+        r.p[0] = pr.p[0]; r.p[1] = pr.p[1]; r.p[2] = pr.p[2]; r.p[3] = pr.p[3];
+        r.u_acc = pr.u_acc; r.pad = 0.0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+        uint4 *dst = reinterpret_cast<uint4 *>(props + t);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     }
 }
 

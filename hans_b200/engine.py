@@ -34,7 +34,7 @@ class WalkerPool:
 
     def __init__(self, nwalkers: int, nchains: int, nbeads: int, move_ratio: Sequence[float],
                  device: Optional[torch.device] = None, seed: int = 0, gid_base: int = 0,
-                 threads_per_walker: int = 0, **cfg_kw):
+                 threads_per_walker: int = 0, workspace_mb: int = 1024, **cfg_kw):
         if not torch.cuda.is_available():
             raise _lib.HansError("hans_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -53,6 +53,10 @@ class WalkerPool:
         self.pair_tests = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.moves_per_sweep = _lib.moves_per_sweep(nbeads, nchains)
         self.launches = 0  # kernels launched through this pool (bench.py reports it)
+        # proposals of a walk are generated ahead of it into this scratch (hans_mc_run_batch_ws);
+        # 0 = generate inside the walk kernel
+        self.workspace_bytes = int(workspace_mb) << 20
+        self._ws: Optional[torch.Tensor] = None
 
     # ---- configuration ------------------------------------------------------------------------
     def set_move_ratio(self, move_ratio) -> None:
@@ -166,11 +170,18 @@ class WalkerPool:
             att = torch.zeros((n, 6), dtype=torch.int64, device=self.device)
             acc = torch.zeros((n, 6), dtype=torch.int64, device=self.device)
         c = self.cfg if cfg is None else cfg
-        check(lib.hans_mc_run_batch(C.byref(c), self.H.data_ptr(), self.R.data_ptr(), self.ctr.data_ptr(), _ptr(d_ids),
-                                    n, int(sweeps), _ptr(d_volume_limit), float(volume_limit), self.seed, self.gid_base,
-                                    _ptr(att), _ptr(acc), self.vol.data_ptr(),
-                                    self.pair_tests.data_ptr() if count_pairs else None, self.tpw, _stream()))
-        self.launches += 1
+        nmoves = int(sweeps) * self.moves_per_sweep
+        need = n * nmoves * PROPOSAL_DTYPE.itemsize
+        ws_bytes = min(need, self.workspace_bytes)
+        if ws_bytes and (self._ws is None or self._ws.numel() < ws_bytes):
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        chunk = (ws_bytes // max(n * PROPOSAL_DTYPE.itemsize, 1)) & ~31
+        check(lib.hans_mc_run_batch_ws(C.byref(c), self.H.data_ptr(), self.R.data_ptr(), self.ctr.data_ptr(), _ptr(d_ids),
+                                       n, int(sweeps), _ptr(d_volume_limit), float(volume_limit), self.seed, self.gid_base,
+                                       _ptr(att), _ptr(acc), self.vol.data_ptr(),
+                                       self.pair_tests.data_ptr() if count_pairs else None, self.tpw,
+                                       _ptr(self._ws) if ws_bytes else None, int(ws_bytes), _stream()))
+        self.launches += 1 if chunk == 0 else 2 * -(-nmoves // chunk)  # (generate + walk) per chunk
         return att, acc
 
     def replay(self, ids, proposals: np.ndarray, volume_limit: float = DBL_MAX, mode: int = MODE_FUSED) -> np.ndarray:

@@ -128,6 +128,26 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
                       uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted,
                       double *d_vol, uint64_t *d_pair_tests, int threads_per_walker, void *stream);
 
+/* The same walk with the proposals generated ahead of it: proposals do not depend on the state, so
+ * hans_gen_proposals (throughput-bound: Philox, Box-Muller, quaternions) fills d_workspace at full
+ * occupancy and the latency-bound walk kernel reads 64 bytes per move instead of computing them on
+ * its critical path.  Same trajectory, bit for bit.  The workspace holds n_active * 64 bytes per
+ * move; if it is smaller than the walk, the walk is cut into chunks (generate, walk, generate, ...);
+ * d_workspace = NULL falls back to generation inside the walk kernel (= hans_mc_run_batch). */
+int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
+                         const int32_t *d_ids, int n_active, int sweeps,
+                         const double *d_volume_limit, double volume_limit, uint64_t seed,
+                         uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted,
+                         double *d_vol, uint64_t *d_pair_tests, int threads_per_walker,
+                         void *d_workspace, uint64_t workspace_bytes, void *stream);
+
+/* d_props[k][m] = proposal number d_ctr[walker k] + m of walker k = d_ids[k], m < nmoves: exactly
+ * the proposals hans_mc_run_batch would draw (four Philox4x32-10 blocks per move
+ * keyed by (seed; counter, gid_base + walker)).  Does not advance d_ctr. */
+int hans_gen_proposals(const hans_cfg *cfg, const uint64_t *d_ctr, const int32_t *d_ids, int n_active,
+                       int nmoves, uint64_t seed, uint32_t gid_base, hans_proposal *d_props,
+                       void *stream);
+
 /* ---- replay: explicit proposals in, decisions out (bit-exact parity entry) -------------------
  * d_props[n_active][nmoves], d_out[n_active][nmoves].  mode = HANS_MODE_FUSED | HANS_MODE_PROPOSE.
  * With HANS_MODE_PROPOSE and nmoves = 1 this IS alk.alkane_translate_chain / alkane_rotate_chain /

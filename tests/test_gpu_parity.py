@@ -211,6 +211,48 @@ def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     assert not pool.check_overlap().cpu().numpy().any()
 
 
+@pytest.mark.parametrize("shape,tpw,ws_moves", [("C2", 0, 0), ("C2", 0, 96), ("C1", 0, 64), ("C1", 32, 32), ("C4s", 128, 0),
+                                                 ("C4s", 128, 160), ("dimer", 1, 32)])
+def test_mc_run_proposals_ahead(eng, oracle, shape, tpw, ws_moves):
+    """hans_mc_run_batch_ws: proposals generated ahead of the walk into a workspace (default), with a
+    workspace so small that the walk is cut into chunks, and without one (generation in the kernel)."""
+    nw, sweeps, seed = 6, 4, 777
+    cfg, H, R, k = make_walkers(shape, nw, seed=13)
+    pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=tpw)
+    pool.workspace_bytes = ws_moves * nw * oracle.PROPOSAL_DTYPE.itemsize
+    limit = float(np.median([oracle.volume(H[w]) for w in range(nw)]))
+    att, acc = pool.mc_run(sweeps, volume_limit=limit)
+    ctrs = np.zeros(nw, dtype=np.uint64)
+    o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, np.arange(nw), sweeps, limit, seed, np.arange(nw), ctrs)
+    assert np.array_equal(att.cpu().numpy().astype(np.uint64), o_att)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+    assert_state_equal(pool, H, R)
+    assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
+
+
+def test_gen_proposals_match_oracle(eng, oracle):
+    """hans_gen_proposals writes exactly the proposals the checker draws."""
+    import ctypes as C
+    from hans_b200 import _lib
+    nchains, nbeads, mr = SHAPES["C1"]
+    pool = eng.WalkerPool(3, nchains, nbeads, [1, 1, 1, 1, 1, 1], seed=99, gid_base=5)
+    pool.ctr += torch.tensor([0, 17, 1 << 33], device=pool.device)
+    nm = 200
+    buf = torch.zeros(2 * nm * oracle.PROPOSAL_DTYPE.itemsize, dtype=torch.uint8, device=pool.device)
+    ids = torch.tensor([2, 1], dtype=torch.int32, device=pool.device)
+    _lib.check(_lib.lib.hans_gen_proposals(C.byref(pool.cfg), pool.ctr.data_ptr(), ids.data_ptr(), 2, nm, 99, 5,
+                                           buf.data_ptr(), None))
+    got = buf.cpu().numpy().view(oracle.PROPOSAL_DTYPE).reshape(2, nm)
+    cfg = oracle.make_cfg(nchains, nbeads, [1, 1, 1, 1, 1, 1])
+    for row, (w, c0) in enumerate([(2, 1 << 33), (1, 17)]):
+        want = oracle.gen_proposals(cfg, 99, 5 + w, c0, nm)
+        for f in ("type", "ichain", "idx0", "idx1"):
+            assert np.array_equal(got[row][f], want[f]), f
+        assert np.array_equal(got[row]["p"].view(np.uint64), want["p"].view(np.uint64))
+        assert np.array_equal(got[row]["u_acc"].view(np.uint64), want["u_acc"].view(np.uint64))
+
+
 def test_mc_run_device_limit_and_no_counters(eng, oracle):
     cfg, H, R, k = make_walkers("C1", 4, seed=8)
     pool = make_pool(eng, "C1", H, R, k, seed=5)

@@ -13,12 +13,14 @@ CASES = {
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 tpws = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [32, 64, 128]
 walk = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+ws_mb = int(sys.argv[4]) if len(sys.argv) > 4 else 1024
 for name in which:
     nc, nb, mr, nw = CASES[name]
     for tpw in tpws:
-        pool = engine.WalkerPool(nw, nc, nb, mr, seed=1, threads_per_walker=tpw)
+        pool = engine.WalkerPool(nw, nc, nb, mr, seed=1, threads_per_walker=tpw, workspace_mb=ws_mb)
         pool.set_initial_cells(); pool.grow()
         pool.mc_run(5, counters=False)
+        pool._ws = torch.empty(min(nw * walk * pool.moves_per_sweep * 64, pool.workspace_bytes), dtype=torch.uint8, device=pool.device) if pool.workspace_bytes else None
         torch.cuda.synchronize()
         lim = float(pool.vol.median().item())
         pool.pair_tests.zero_()
@@ -30,5 +32,5 @@ for name in which:
         moves = nw * walk * pool.moves_per_sweep
         pt = int(pool.pair_tests.item())
         rate = (acc.sum(0).double() / att.sum(0).clamp(min=1).double()).cpu().numpy().round(3)
-        print(json.dumps(dict(case=name, tpw=tpw, ms=round(ms, 2), moves_per_s=round(moves / ms * 1e3 / 1e6, 2), unit="M/s",
+        print(json.dumps(dict(case=name, tpw=tpw, ws_mb=ws_mb, ms=round(ms, 2), moves_per_s=round(moves / ms * 1e3 / 1e6, 2), unit="M/s",
                               pair_tests_per_s=round(pt / ms * 1e3 / 1e9, 2), pairs_per_move=round(pt / moves, 1), acc=list(rate))), flush=True)
