@@ -308,7 +308,6 @@ template <bool REPLAY> static int launch_lean(const WalkArgs &a, int W, cudaStre
         walk_lean_kernel<NN, WW, REPLAY><<<spec_grid(a.n_active), 32, smem, st>>>(a);     \
     })
     if (W == 1) { LEAN_LAUNCH(1); }
-    else if (W == 4) { LEAN_LAUNCH(4); }
     else { LEAN_LAUNCH(8); }
 #undef LEAN_LAUNCH
     CK(cudaGetLastError());
@@ -320,7 +319,7 @@ static int pick_W(const hans_cfg *c, int tpw)
 {
     if (tpw >= 32 || !lean_applies(c)) return -1;
     if (tpw == 0) return hans_default_window(c);
-    return (tpw == 1 || tpw == 4 || tpw == 8) ? tpw : -1;
+    return (tpw == 1 || tpw == 8) ? tpw : -1;
 }
 
 #define DISPATCH_T(T, ...)                                    \
@@ -369,7 +368,11 @@ int hans_default_threads_per_walker(const hans_cfg *cfg)
 int hans_default_window(const hans_cfg *cfg)
 {
     if (!cfg || !lean_applies(cfg)) return 0;
-    return cfg->nchains >= 4 ? 8 : 1; // windows need several chains to spread the moves over
+    // Measured on B200 (profiles/r01_*): with the proposals generated ahead and the code footprint
+    // inside the instruction cache, one move at a time beats the speculative windows at every
+    // BASELINE shape -- phase B costs as many instructions per accepted move as a serial move.
+    // The windows stay available through threads_per_walker = 8.
+    return 1;
 }
 
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
@@ -379,10 +382,10 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         const int W = pick_W(cfg, threads_per_walker);
         if (W > 0) return from_memory ? launch_lean<true>(a, W, st) : launch_lean<false>(a, W, st);
         if (threads_per_walker != 0)
-            return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 4, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
+            return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
     }
     const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 4, 8, 32, 64, 128 or 256");
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 32, 64, 128 or 256");
     const size_t smem = cta_smem_bytes(cfg, T);
     if (from_memory) {
         DISPATCH_T(T, {
@@ -439,9 +442,10 @@ int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t
     cudaStream_t st = (cudaStream_t)stream;
     // moves per chunk the workspace holds (a multiple of 32: the kernels take proposals 32 at a time)
     const uint64_t per_move = (uint64_t)n_active * sizeof(hans_proposal);
-    uint64_t chunk = d_workspace ? (workspace_bytes / per_move) & ~(uint64_t)31 : 0;
-    if (chunk == 0) return launch_walk(cfg, a, false, threads_per_walker, st); // no workspace: generate in the kernel
     const int total = a.nmoves;
+    uint64_t chunk = d_workspace ? workspace_bytes / per_move : 0;
+    if (chunk < (uint64_t)total) chunk &= ~(uint64_t)31; else chunk = (uint64_t)total;
+    if (chunk == 0) return launch_walk(cfg, a, false, threads_per_walker, st); // no workspace: generate in the kernel
     for (int m0 = 0; m0 < total; m0 += (int)chunk) {
         const int n = total - m0 < (int)chunk ? total - m0 : (int)chunk;
         rc = hans_gen_proposals(cfg, d_ctr, d_ids, n_active, n, seed, gid_base, (hans_proposal *)d_workspace, stream);

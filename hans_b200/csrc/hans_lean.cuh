@@ -47,12 +47,13 @@ __device__ __noinline__ bool lean_recheck(WCtx w, int ichain, int b0, bool amb, 
 }
 
 // cold: chain moves that are not on the fast path of their specialisation
-__device__ __noinline__ Dec lean_move_chain_generic(WCtx w, int q, unsigned *pairs)
+__device__ __noinline__ DecP lean_move_chain_generic(WCtx w, int q)
 {
     unsigned pr = 0;
     const Dec d = move_chain<32>(w, W_RING(w) + q, HANS_MODE_FUSED, pr);
-    *pairs += pr;
-    return d;
+    DecP o;
+    o.accepted = d.accepted; o.reason = d.reason; o.boltz = d.boltz; o.pairs = pr;
+    return o;
 }
 
 // single spheres (NB == 1), translation: alk.alkane_translate_chain + accept/restore
@@ -344,7 +345,10 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
             }
             __syncwarp();
             const unsigned plain = W > 1 ? __ballot_sync(FULL, my_plain) : 0u;
-            int my_acc = 0, my_reason = 0;
+            // decisions of the batch: accepted bits (uniform); reason / boltz of the moves that are not
+            // plain single-chain moves are kept by lane q (a chain move's follow from its bit)
+            unsigned accmask = 0;
+            int my_reason = -1;
             double my_boltz = 0.0;
             for (int q = 0; q < nbatch; ++q) {
                 if (W > 1) { // a run of at least two plain single-chain moves: settle it as a window
@@ -354,12 +358,7 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
                     if (nw >= 2) {
                         unsigned ab;
                         const int done = lean_window<NB, (W > 1 ? W : 4)>(w, cr, q, nw, ab, pairs);
-                        const int rel = w.lane - q;
-                        if (rel >= 0 && rel < done) {
-                            my_acc = (int)((ab >> rel) & 1u);
-                            my_reason = my_acc ? HANS_ACCEPT : HANS_REJ_OVERLAP;
-                            my_boltz = my_acc ? 1.0 : 0.0;
-                        }
+                        accmask |= ab << q;
                         q += done - 1;
                         continue;
                     }
@@ -367,28 +366,29 @@ __global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
                 const PropRec *p = ring + q;
                 const int4 hd = *reinterpret_cast<const int4 *>(p); // type, ichain, idx0, idx1
                 const int type = hd.x, ichain = hd.y;
-                int accepted, reason;
-                double boltz;
                 const bool chain_ok = (unsigned)ichain < (unsigned)w.nc;
                 if (NB == 1 && type == HANS_TRANS && chain_ok) {
-                    accepted = lean_translate_sphere(w, cr, p, ichain, pairs);
-                    reason = accepted ? HANS_ACCEPT : HANS_REJ_OVERLAP; boltz = accepted ? 1.0 : 0.0;
+                    accmask |= (unsigned)lean_translate_sphere(w, cr, p, ichain, pairs) << q;
                 } else if (NB > 1 && chain_ok &&
                            (type == HANS_TRANS || type == HANS_ROT || (type == HANS_DIH && NB >= 4 && hd.z >= 3 && hd.z <= NB - 1))) {
-                    accepted = lean_move_chain<(NB > 1 ? NB : 2)>(w, cr, p, ichain, pairs);
-                    reason = accepted ? HANS_ACCEPT : HANS_REJ_OVERLAP; boltz = accepted ? 1.0 : 0.0;
-                } else if (type >= HANS_TRANS && type <= HANS_DIH) {
-                    const Dec d = lean_move_chain_generic(w, q, &pairs);
-                    accepted = d.accepted; reason = d.reason; boltz = d.boltz;
+                    accmask |= (unsigned)lean_move_chain<(NB > 1 ? NB : 2)>(w, cr, p, ichain, pairs) << q;
                 } else {
-                    const DecP d = move_box<T>(w, q, limit, HANS_MODE_FUSED);
-                    accepted = d.accepted; reason = d.reason; boltz = d.boltz; pairs += d.pairs;
-                    cr = load_cell_regs(w); // the cell may have changed (also on a reverted shear / stretch)
+                    DecP d;
+                    if (type >= HANS_TRANS && type <= HANS_DIH) {
+                        d = lean_move_chain_generic(w, q);
+                    } else {
+                        d = move_box<T>(w, q, limit, HANS_MODE_FUSED);
+                        cr = load_cell_regs(w); // the cell may have changed (also on a reverted shear / stretch)
+                    }
+                    pairs += d.pairs;
+                    accmask |= (d.accepted ? 1u : 0u) << q;
+                    if (w.lane == q) { my_reason = d.reason; my_boltz = d.boltz; }
                 }
-                if (w.lane == q) { my_acc = accepted; my_reason = reason; my_boltz = boltz; }
             }
             pairs_total += pairs;
             pairs = 0;
+            const int my_acc = (int)((accmask >> w.lane) & 1u);
+            if (my_reason < 0) { my_reason = my_acc ? HANS_ACCEPT : HANS_REJ_OVERLAP; my_boltz = my_acc ? 1.0 : 0.0; }
             if (my_type >= 0) {
 #pragma unroll
                 for (int t = 0; t < 6; ++t) { att[t] += (my_type == t); acc[t] += (my_type == t && my_acc); }

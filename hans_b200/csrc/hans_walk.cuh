@@ -467,10 +467,10 @@ __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, un
         const int dse = nb - 1 - (ii % nb);                                   // d <= dse: same chain
         const int dmax = row_on ? half - ((even && ii >= half) ? 1 : 0) : 0;  // offsets this lane owns
         int namb = 0, aj0 = 0, aj1 = 0; // pairs of this row that fell into the band (first two kept)
-        for (int d0 = 1 + dg; d0 <= half; d0 += DG * U) {
+        for (int d0 = 1; d0 <= half; d0 += DG * U) { // (lane-uniform trip count: the vote below is a collective)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int d = d0 + u * DG;
+                const int d = d0 + dg + u * DG;
                 int j = ii + d;
                 if (j >= N) j -= N;
                 const bool valid = (d <= dmax) && ((d > dse) || (d > nex_eff));

@@ -102,7 +102,7 @@ int hans_moves_per_sweep(int nbeads, int nchains);
 /* default threads per walker for a shape (32 = one warp per walker, else one CTA per walker) */
 int hans_default_threads_per_walker(const hans_cfg *cfg);
 /* window size the warp-per-walker kernel uses for a shape when threads_per_walker = 0 (1 = one
- * move at a time, 4 / 8 = speculative windows); 0 = the shape runs on the cooperative kernel */
+ * move at a time, 8 = speculative windows); 0 = the shape runs on the cooperative kernel */
 int hans_default_window(const hans_cfg *cfg);
 
 /* ---- the fused hot path ---------------------------------------------------------------------
@@ -115,9 +115,9 @@ int hans_default_window(const hans_cfg *cfg);
  * d_pair_tests        device scalar, executed pair tests accumulated (may be NULL)
  * threads_per_walker  32, 64, 128, 256: cooperative kernel, the walker's threads share every move
  *                     (32 = one warp per walker, else one CTA per walker);
- *                     1, 4, 8: warp-per-walker kernel specialised on nbeads (needs nchains*nbeads
- *                     <= 128, nbeads in {1,2,4,6,8,12}); 1 = one move at a time, 4 / 8 = speculative
- *                     windows of that many consecutive single-chain moves, settled in order (same
+ *                     1, 8: warp-per-walker kernel specialised on nbeads (needs nchains*nbeads
+ *                     <= 128, nbeads in {1,2,4,6,8,12}); 1 = one move at a time, 8 = speculative
+ *                     windows of up to 8 consecutive single-chain moves, settled in order (same
  *                     decisions and trajectory, bit for bit);
  *                     0 = hans_default_window if the shape qualifies, else
  *                     hans_default_threads_per_walker
