@@ -95,55 +95,23 @@ __device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRe
     return overlap ? 0 : 1;
 }
 
-// chains of NB beads: translate / rotate / dihedral with the trial shadows in registers
+// chains of NB beads: translate / rotate / dihedral; chain-level pruning, trial shadows in registers
 template <int NB>
 __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr, const PropRec *p, int ichain,
                                                unsigned &pairs)
 {
-    const int c0 = ichain * NB, cn = W_CN(w), c4 = W_C4(w), f4 = W_F4(w), N = w.N;
+    const int c0 = ichain * NB, cn = W_CN(w), c4 = W_C4(w), f4 = W_F4(w);
     int b0 = 0;
     bool intra = false;
     make_trial(w, p, w.lane, 32, cn, c4, b0, intra); // (proposal validated by the caller)
     __syncwarp();
-    float4 c[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) c[b] = SM4[c4 + b];
-    const Filt &f = cr.f;
-    bool ov = false, amb = false;
-    for (int j = w.lane; j < N; j += 32) {
-        if ((unsigned)(j - c0) >= (unsigned)NB) {
-            const float4 s = SM4[f4 + j];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float r2 = r2_f32(f, s.x - c[b].x, s.y - c[b].y, s.z - c[b].z);
-                const bool moved = b >= b0;
-                ov |= moved && (r2 < f.lo);
-                amb |= moved && !(r2 > f.hi);
-            }
-            pairs += (unsigned)(NB - b0);
-        }
-    }
-    bool amb_intra = false;
-    if (intra) {
-        const uchar2 *tab = W_ITAB(w);
-        for (int e = w.lane; e < w.npc; e += 32) {
-            const uchar2 jb = tab[e];
-            if ((int)jb.y >= b0) {
-                const float4 a = SM4[c4 + jb.x], b = SM4[c4 + jb.y];
-                const float r2 = r2_f32(f, b.x - a.x, b.y - a.y, b.z - a.z);
-                ov |= (r2 < f.lo);
-                amb_intra |= !(r2 > f.hi);
-                pairs += 1;
-            }
-        }
-    }
-    const unsigned code = __reduce_or_sync(FULL, (ov ? 4u : 0u) | (amb ? 1u : 0u) | (amb_intra ? 2u : 0u));
-    bool overlap = (code & 4u) != 0u;
-    if (!overlap && code) overlap = lean_recheck(w, ichain, b0, amb, amb_intra);
-    if (!overlap && (p->u_acc < 1.0)) {
+    const float Rt = intra ? chain_radius(cn, NB) : SMF[w.rad + ichain]; // translations and rotations are rigid
+    const bool overlap = chain_overlaps_pruned<32, NB>(w, cr.f, ichain, b0, intra, Rt, pairs);
+    if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
         const int P = W_P(w) + 3 * c0;
         for (int k = w.lane; k < 3 * NB; k += 32) smem[P + k] = smem[cn + k];
         for (int k = w.lane; k < NB; k += 32) SM4[f4 + c0 + k] = SM4[c4 + k];
+        if (intra && w.lane == 0) SMF[w.rad + ichain] = Rt;
     }
     __syncwarp();
     return overlap ? 0 : 1;
@@ -267,6 +235,7 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
             const int P = W_P(w) + 3 * NB * ci, f4c = f4 + NB * ci;
             for (int e = lane; e < 3 * NB; e += 32) smem[P + e] = smem[wci + e];
             for (int e = lane; e < NB; e += 32) SM4[f4c + e] = SM4[w4i + e];
+            if (NB > 1 && pi->type == HANS_DIH && lane == 0) SMF[w.rad + ci] = chain_radius(wci, NB);
         }
         __syncwarp();
         if (!pend) break;

@@ -63,8 +63,11 @@ struct WCtx {
     int ring; // PropRec index (64-byte units from the start of shared memory)
     int itab; // uchar2 index of the intra-chain pair table
     int cfg;  // double index of the CTA's copy of hans_cfg
-    int wc;   // speculative windows (hans_spec.cuh): double index of the W trial chains [W][3nb]
+    int wc;   // speculative windows (hans_lean.cuh): double index of the W trial chains [W][3nb]
     int w4;   //                                      float4 index of their shadows [W][nb]
+    int rad;  // float index of the chain bounding radii RAD[nc]
+    int lst;  // int index of the near list LST[T] (+ its counter at lst - 1 ... see near_list())
+    unsigned nbmagic, ncmagic; // x / nb = umulhi(x, nbmagic), x / nc = umulhi(x, ncmagic) for x < 2^16
 };
 #define W_P(w) ((w).D0)
 #define W_TP(w) ((w).D0 + 3 * (w).N)
@@ -74,6 +77,7 @@ struct WCtx {
 #define W_G4(w) ((w).Q0 + (w).N)
 #define W_C4(w) ((w).Q0 + 2 * (w).N)
 #define W_SF(w) (4 * ((w).Q0 + 2 * (w).N + (w).nb))
+#define SF_TRIAL 16 /* float offset of the trial cell's filter parameters behind the current cell's */
 #define W_RING(w) (reinterpret_cast<PropRec *>(smem) + (w).ring)
 #define W_ITAB(w) (reinterpret_cast<const uchar2 *>(smem) + (w).itab)
 #define W_CFG(w) (reinterpret_cast<const hans_cfg *>(smem + (w).cfg))
@@ -89,7 +93,9 @@ __host__ __device__ inline size_t walker_smem_bytes(int N, int nb, int T)
 {
     size_t b = sizeof(double) * ((size_t)6 * N + (size_t)3 * nb + 36);
     b = (b + 15) & ~(size_t)15;
-    b += 16 * ((size_t)2 * N + nb) + 64; // float4 shadows + SF
+    b += 16 * ((size_t)2 * N + nb) + 128; // float4 shadows + SF (2 x 16 floats)
+    b += (((size_t)4 * (N / nb)) + 15) & ~(size_t)15; // RAD
+    b += 16 + 4 * (size_t)T;              // near-list counter + LST
     b = (b + 63) & ~(size_t)63;
     b += 64 * (size_t)T;                 // ring
     return b;
@@ -123,6 +129,13 @@ __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W)
     const int dbytes = ((8 * (6 * w.N + 3 * w.nb + 36)) + 15) & ~15;
     w.Q0 = (base + dbytes) / 16;
     w.ring = (base + core - 64 * T) / 64;
+    {
+        const int sf_end = 16 * (w.Q0 + 2 * w.N + w.nb) + 128;          // bytes
+        w.rad = sf_end / 4;
+        w.lst = (sf_end + ((4 * w.nc + 15) & ~15) + 16) / 4;
+    }
+    w.nbmagic = 0xFFFFFFFFu / (unsigned)w.nb + 1u;
+    w.ncmagic = 0xFFFFFFFFu / (unsigned)w.nc + 1u;
     w.wc = (base + core) / 8;
     w.w4 = (base + core + 24 * W * w.nb + 15) / 16;
     const int extra = per * GPC;
@@ -166,7 +179,8 @@ template <int T> __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
 // those terms and carries a further safety factor.  The filter is
 // switched off (every pair is re-tested in float64) when a perpendicular width is <= 2.1, where
 // float32 and float64 could wrap a pair to different images that both lie within reach of sigma.
-// SF layout: g00, g11, g22, 2 g01, 2 g02, 2 g12, lo = 1 - eps, hi = 1 + eps.
+// SF layout: g00, g11, g22, 2 g01, 2 g02, 2 g12, lo = 1 - eps, hi = 1 + eps, hw = (half the smallest
+// perpendicular width, rounded down): separations below hw are wrapped to their nearest image.
 // ---------------------------------------------------------------------------------------------
 __device__ __noinline__ void filter_params(int sh, int sf, bool writer)
 {
@@ -187,15 +201,17 @@ __device__ __noinline__ void filter_params(int sh, int sf, bool writer)
         o[0] = (float)g00; o[1] = (float)g11; o[2] = (float)g22;
         o[3] = (float)(2.0 * g01); o[4] = (float)(2.0 * g02); o[5] = (float)(2.0 * g12);
         o[6] = lo; o[7] = hi;
+        o[8] = (float)((0.5 / sqrt(B2)) * (1.0 - 1e-6));
     }
 }
 
-struct Filt { float g00, g11, g22, g01, g02, g12, lo, hi; };
+struct Filt { float g00, g11, g22, g01, g02, g12, lo, hi, hw; };
 __device__ __forceinline__ Filt load_filt(int sf)
 {
     const float4 a = SM4[sf / 4], b = SM4[sf / 4 + 1];
     Filt f;
     f.g00 = a.x; f.g11 = a.y; f.g22 = a.z; f.g01 = a.w; f.g02 = b.x; f.g12 = b.y; f.lo = b.z; f.hi = b.w;
+    f.hw = SMF[sf + 8];
     return f;
 }
 
@@ -363,6 +379,133 @@ __device__ __forceinline__ bool make_trial(const WCtx &w, const PropRec *p, int 
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chain-level pruning (chains of more than one bead).
+//
+// Every chain c carries a bounding sphere: centre = its middle bead (whose float32 shadow is already
+// in F4 / G4 / C4), radius RAD[c] = the largest float64 distance of a bead from it, rounded up.  Two
+// chains can only have a bead pair closer than sigma = 1 if their centres are closer than
+// D = R_a + R_b + 1, so a pair of chains whose float32 centre separation exceeds D by a margin
+// (0.001 in D and 1e-5 relative in D^2, orders of magnitude above the float32 error of the shadows
+// and of the metric) is skipped WITHOUT testing its beads; only the chains that survive go through
+// the bead-level float32 filter / float64 settle above.  The test is valid while D is below half the
+// smallest perpendicular width of the cell (`hw`): then the wrapped fractional separation of the
+// centres is their nearest image, and so is that of every bead pair within sigma.  For smaller
+// cells nothing is skipped.  Skipped pairs are certain non-overlaps, so decisions -- and with them
+// whole trajectories -- are unchanged; only the number of executed pair tests drops (hexamers in
+// the dilute regime: 540 -> ~60 per chain move).  This is the role hs_alkane's link cells play
+// (bypassed by the reference, MCNS.py:603), at chain granularity.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float chain_radius(int pos, int nb)
+{
+    const int m = nb >> 1;
+    const double mx = smem[pos + 3 * m], my = smem[pos + 3 * m + 1], mz = smem[pos + 3 * m + 2];
+    double r2 = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        const double dx = smem[pos + 3 * b] - mx, dy = smem[pos + 3 * b + 1] - my, dz = smem[pos + 3 * b + 2] - mz;
+        const double d2 = (dx * dx + dy * dy) + dz * dz;
+        r2 = d2 > r2 ? d2 : r2;
+    }
+    return __fsqrt_ru(__double2float_ru(r2));
+}
+
+__device__ __forceinline__ bool spheres_near(const Filt &f, const float4 a, const float4 b, float D)
+{
+    const float r2c = r2_f32(f, a.x - b.x, a.y - b.y, a.z - b.z);
+    return !(D < f.hw) || !(r2c > D * D * 1.00001f);
+}
+
+// Compaction of the items a wave of T threads flags `near` into LST; returns their number.
+// Collective over the group; the group must synchronise (gsync / gany) before the next call.
+template <int T>
+__device__ __forceinline__ int near_list(const WCtx &w, bool near, int item)
+{
+    int *lst = reinterpret_cast<int *>(smem) + w.lst;
+    if (T == 32) {
+        const unsigned mask = __ballot_sync(FULL, near);
+        if (near) lst[__popc(mask & ((1u << w.lane) - 1u))] = item;
+        __syncwarp();
+        return __popc(mask);
+    } else {
+        int *cnt = lst - 4;
+        if (w.lane == 0) *cnt = 0;
+        __syncthreads();
+        if (near) lst[atomicAdd(cnt, 1)] = item;
+        __syncthreads();
+        return *cnt;
+    }
+}
+
+// Does the trial chain (CN / C4, bounding radius Rt) overlap anything?  NB > 0: beads per chain known
+// at compile time, trial shadows in registers.
+template <int T, int NB>
+__device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt &f, int ichain, int b0, bool intra,
+                                                      float Rt, unsigned &pairs)
+{
+    const int nb = NB ? NB : w.nb, nc = w.nc, m = nb >> 1, f4 = W_F4(w), c4 = W_C4(w);
+    const int *lst = reinterpret_cast<const int *>(smem) + w.lst;
+    float4 tr[NB ? NB : 1];
+    if (NB) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tr[b] = SM4[c4 + b];
+    }
+    const float4 ct = SM4[c4 + m];
+    bool ov = false, amb = false;
+    for (int cb = 0; cb < nc; cb += T) {
+        const int c = cb + w.lane;
+        bool near = false;
+        if (c < nc && c != ichain) near = spheres_near(f, SM4[f4 + c * nb + m], ct, Rt + SMF[w.rad + c] + 1.001f);
+        const int items = near_list<T>(w, near, c) * nb;
+        for (int e = w.lane; e < items; e += T) {
+            const int ci = NB ? e / (NB ? NB : 1) : (int)__umulhi((unsigned)e, w.nbmagic);
+            const float4 s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
+            if (NB) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float r2 = r2_f32(f, s.x - tr[b].x, s.y - tr[b].y, s.z - tr[b].z);
+                    const bool moved = b >= b0;
+                    ov |= moved && (r2 < f.lo);
+                    amb |= moved && !(r2 > f.hi);
+                }
+            } else {
+                for (int b = b0; b < nb; ++b) {
+                    const float4 t = SM4[c4 + b];
+                    const float r2 = r2_f32(f, s.x - t.x, s.y - t.y, s.z - t.z);
+                    ov |= (r2 < f.lo);
+                    amb |= !(r2 > f.hi);
+                }
+            }
+            pairs += (unsigned)(nb - b0);
+        }
+        pairs += (c < nc) ? 1u : 0u;
+        if (cb + T < nc) gsync<T>(); // LST is rewritten by the next wave
+    }
+    bool amb_intra = false;
+    if (intra) {
+        const uchar2 *tab = W_ITAB(w);
+        for (int e = w.lane; e < w.npc; e += T) {
+            const uchar2 jb = tab[e];
+            if ((int)jb.y >= b0) {
+                const float4 p = SM4[c4 + jb.x], q = SM4[c4 + jb.y];
+                const float r2 = r2_f32(f, q.x - p.x, q.y - p.y, q.z - p.z);
+                ov |= (r2 < f.lo);
+                amb_intra |= !(r2 > f.hi);
+                pairs += 1;
+            }
+        }
+    }
+    if (T == 32) {
+        const unsigned code = __reduce_or_sync(FULL, (ov ? 4u : 0u) | (amb ? 1u : 0u) | (amb_intra ? 2u : 0u));
+        if (code & 4u) return true;
+        if (code) return __any_sync(FULL, recheck_chain_exact<T>(w, ichain, b0, (code & 1u) != 0u, (code & 2u) != 0u));
+        return false;
+    }
+    if (gany<T>(ov)) return true;
+    const bool any_inter = gany<T>(amb), any_intra = intra && gany<T>(amb_intra);
+    if (any_inter || any_intra) return gany<T>(recheck_chain_exact<T>(w, ichain, b0, any_inter, any_intra));
+    return false;
+}
+
 // translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
 // alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
 template <int T>
@@ -374,7 +517,14 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
     bool intra = false;
     if (!make_trial(w, p, w.lane, T, cn, c4, b0, intra)) return mkdec(0, HANS_REJ_INVALID, 0.0);
     gsync<T>();
-    const bool ov = chain_overlaps<T>(w, ichain, b0, intra, pairs);
+    bool ov;
+    float Rt = 0.0f;
+    if (nb > 1) {
+        Rt = intra ? chain_radius(cn, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
+        ov = chain_overlaps_pruned<T, 0>(w, load_filt(W_SF(w)), ichain, b0, intra, Rt, pairs);
+    } else {
+        ov = chain_overlaps<T>(w, ichain, b0, intra, pairs);
+    }
     const double boltz = ov ? 0.0 : 1.0;
     if ((mode == HANS_MODE_PROPOSE) || (p->u_acc < boltz)) { // MCNS.py:372
         const int f4 = W_F4(w) + c0;
@@ -382,6 +532,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
             smem[P + 3 * b] = smem[cn + 3 * b]; smem[P + 3 * b + 1] = smem[cn + 3 * b + 1]; smem[P + 3 * b + 2] = smem[cn + 3 * b + 2];
             SM4[f4 + b] = SM4[c4 + b];
         }
+        if (intra && w.lane == 0) SMF[w.rad + ichain] = Rt;
     }
     gsync<T>();
     return mkdec(ov ? 0 : 1, ov ? HANS_REJ_OVERLAP : HANS_ACCEPT, boltz);
@@ -441,6 +592,82 @@ __device__ __noinline__ bool trial_overlap_exact(WCtx w, bool with_intra)
     return all_overlap64<T>(w, W_TP(w), H, Hi, with_intra);
 }
 
+// Box moves of chain systems: all pairs of CHAINS through their bounding spheres (round robin over
+// the chains: item p = (row ci, offset d), cj = ci + d mod nc), bead level only for the pairs of
+// chains that survive, one wave of T chain pairs at a time.  Pairs of beads inside the filter's band
+// are settled in float64 at the end (first one per thread; more than one -> the full float64 pass).
+template <int T>
+__device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_intra, unsigned &pairs)
+{
+    const Filt f = load_filt(W_SF(w) + SF_TRIAL);
+    const int nb = w.nb, nc = w.nc, m = nb >> 1, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18;
+    const int half = nc >> 1, nitems = nc * half;
+    const bool even = (nc & 1) == 0;
+    const int *lst = reinterpret_cast<const int *>(smem) + w.lst;
+    bool ov = false;
+    int namb = 0, ai = 0, aj = 0;
+    for (int p0 = 0; p0 < nitems; p0 += T) {
+        const int p = p0 + w.lane;
+        bool near = false;
+        int packed = 0;
+        if (p < nitems) {
+            const int d1 = (int)__umulhi((unsigned)p, w.ncmagic); // offset - 1
+            const int ci = p - d1 * nc, d = d1 + 1;
+            int cj = ci + d;
+            if (cj >= nc) cj -= nc;
+            if (!(even && d == half && ci >= half)) {
+                near = spheres_near(f, SM4[g4 + ci * nb + m], SM4[g4 + cj * nb + m], SMF[w.rad + ci] + SMF[w.rad + cj] + 1.001f);
+                packed = (ci << 16) | cj;
+                pairs += 1;
+            }
+        }
+        const int items = near_list<T>(w, near, packed) * nb;
+        for (int e = w.lane; e < items; e += T) {
+            const int pi = (int)__umulhi((unsigned)e, w.nbmagic);
+            const int pk = lst[pi];
+            const int bi = (pk >> 16) * nb + (e - pi * nb), cj0 = (pk & 0xffff) * nb;
+            const float4 s = SM4[g4 + bi];
+            for (int b = 0; b < nb; ++b) {
+                const float4 t = SM4[g4 + cj0 + b];
+                const float r2 = r2_f32(f, s.x - t.x, s.y - t.y, s.z - t.z);
+                ov |= (r2 < f.lo);
+                if (!(r2 < f.lo) && !(r2 > f.hi)) {
+                    if (namb == 0) { ai = bi; aj = cj0 + b; }
+                    ++namb;
+                }
+            }
+            pairs += (unsigned)nb;
+        }
+        if (gany<T>(ov)) return true; // (also the barrier before LST is rewritten)
+    }
+    if (with_intra && w.npc > 0) { // same-chain pairs further apart than nexclude (shear / stretch, MCNS.py:198,247)
+        const uchar2 *tab = W_ITAB(w);
+        const int total = nc * w.npc;
+        for (int e = w.lane; e < total; e += T) {
+            const int c = e / w.npc;
+            const uchar2 jb = tab[e - c * w.npc];
+            const int bi = c * nb + jb.x, bj = c * nb + jb.y;
+            const float4 s = SM4[g4 + bi], t = SM4[g4 + bj];
+            const float r2 = r2_f32(f, s.x - t.x, s.y - t.y, s.z - t.z);
+            ov |= (r2 < f.lo);
+            if (!(r2 < f.lo) && !(r2 > f.hi)) {
+                if (namb == 0) { ai = bi; aj = bj; }
+                ++namb;
+            }
+            pairs += 1;
+        }
+        if (gany<T>(ov)) return true;
+    }
+    if (gany<T>(namb > 0)) {
+        if (namb > 0)
+            ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj] - smem[tp + 3 * ai], smem[tp + 3 * aj + 1] - smem[tp + 3 * ai + 1],
+                          smem[tp + 3 * aj + 2] - smem[tp + 3 * ai + 2]) < 1.0;
+        if (gany<T>(ov)) return true;
+        if (gany<T>(namb > 1)) return trial_overlap_exact<T>(w, with_intra);
+    }
+    return false;
+}
+
 // all pairs of the TRIAL beads through the float32 filter: same enumeration, branch-free inner
 // loop (8 independent pair tests per lane between votes); pairs inside the band are settled by
 // one float64 pass afterwards, and only if nothing overlapped for certain.
@@ -448,7 +675,8 @@ template <int T>
 __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
 {
     if (w.nc == 1) return trial_overlap_exact<T>(w, with_intra);
-    const Filt f = load_filt(W_SF(w) + 8);
+    if (w.nb > 1) return trial_overlap_pruned<T>(w, with_intra, pairs);
+    const Filt f = load_filt(W_SF(w) + SF_TRIAL);
     const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w);
     const bool even = (N & 1) == 0;
     const int RB = T < N ? T : N;
@@ -530,7 +758,7 @@ template <int T> __device__ __forceinline__ void commit_trial(const WCtx &w)
     for (int i = w.lane; i < 3 * w.N; i += T) smem[p + i] = smem[tp + i];
     for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = SM4[g4 + i];
     if (w.lane < 18) smem[sh + w.lane] = smem[sh + 18 + w.lane];
-    if (w.lane < 8) SMF[sf + w.lane] = SMF[sf + 8 + w.lane];
+    if (w.lane < 9) SMF[sf + w.lane] = SMF[sf + SF_TRIAL + w.lane];
     gsync<T>();
 }
 
@@ -613,7 +841,7 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
     }
     gsync<T>();
     follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), sh + 9, sh + 18, sh + 27); // alk.alkane_change_box, MCNS.py:186,238
-    filter_params(sh + 18, W_SF(w) + 8, w.lane == 0);
+    filter_params(sh + 18, W_SF(w) + SF_TRIAL, w.lane == 0);
     gsync<T>();
     int reason = HANS_ACCEPT;
     if (!is_vol) {
@@ -667,6 +895,8 @@ __device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, con
     if (shadows) {
         const int f4 = W_F4(w);
         for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = shadow_of(smem[p + 3 * i], smem[p + 3 * i + 1], smem[p + 3 * i + 2], smem + sh + 9);
+        if (w.nb > 1)
+            for (int c = w.lane; c < w.nc; c += T) SMF[w.rad + c] = chain_radius(p + 3 * c * w.nb, w.nb);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
     }

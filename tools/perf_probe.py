@@ -9,6 +9,7 @@ CASES = {
     "C3_1024": (16, 6, [3, 48, 32, 0, 3, 3], 1024),
     "C3_4096": (16, 6, [3, 48, 32, 0, 3, 3], 4096),
     "C4_512": (32, 12, [3, 32, 32, 16, 3, 3], 512),
+    "C5_256": (128, 6, [1, 384, 256, 384, 3, 3], 256),
 }
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
 tpws = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [32, 64, 128]
