@@ -82,6 +82,10 @@ struct WCtx {
 #define W_ITAB(w) (reinterpret_cast<const uchar2 *>(smem) + (w).itab)
 #define W_CFG(w) (reinterpret_cast<const hans_cfg *>(smem + (w).cfg))
 
+// x / nb and x / nc for 0 <= x < 2^16 without an integer division (the magic overflows for a divisor of 1)
+__device__ __forceinline__ int div_nb(const WCtx &w, int x) { return w.nb == 1 ? x : (int)__umulhi((unsigned)x, w.nbmagic); }
+__device__ __forceinline__ int div_nc(const WCtx &w, int x) { return w.nc == 1 ? x : (int)__umulhi((unsigned)x, w.ncmagic); }
+
 __host__ __device__ inline int intra_pairs_per_chain(int nb, int nex)
 {
     const int m = nb - nex - 1;
@@ -255,8 +259,10 @@ __device__ __noinline__ bool recheck_chain_exact(WCtx w, int ichain, int b0, boo
     bool ov = false;
     if (w.lane == 0) atomicAdd(&g_diag[0], 1ull);
     if (amb_inter) {
+#pragma unroll 1
         for (int j = w.lane; j < w.N; j += T) {
             if ((unsigned)(j - c0) < (unsigned)nb) continue;
+#pragma unroll 1
             for (int b = b0; b < nb; ++b)
                 ov |= pair_r2(smem + sh, smem + sh + 9, smem[p + 3 * j] - smem[cn + 3 * b],
                               smem[p + 3 * j + 1] - smem[cn + 3 * b + 1], smem[p + 3 * j + 2] - smem[cn + 3 * b + 2]) < 1.0;
@@ -264,6 +270,7 @@ __device__ __noinline__ bool recheck_chain_exact(WCtx w, int ichain, int b0, boo
     }
     if (amb_intra) {
         const uchar2 *tab = W_ITAB(w);
+#pragma unroll 1
         for (int e = w.lane; e < w.npc; e += T) {
             const uchar2 jb = tab[e];
             if ((int)jb.y >= b0)
@@ -401,6 +408,7 @@ __device__ __forceinline__ float chain_radius(int pos, int nb)
     const int m = nb >> 1;
     const double mx = smem[pos + 3 * m], my = smem[pos + 3 * m + 1], mz = smem[pos + 3 * m + 2];
     double r2 = 0.0;
+#pragma unroll 1
     for (int b = 0; b < nb; ++b) {
         const double dx = smem[pos + 3 * b] - mx, dy = smem[pos + 3 * b + 1] - my, dz = smem[pos + 3 * b + 2] - mz;
         const double d2 = (dx * dx + dy * dy) + dz * dz;
@@ -457,7 +465,7 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
         if (c < nc && c != ichain) near = spheres_near(f, SM4[f4 + c * nb + m], ct, Rt + SMF[w.rad + c] + 1.001f);
         const int items = near_list<T>(w, near, c) * nb;
         for (int e = w.lane; e < items; e += T) {
-            const int ci = NB ? e / (NB ? NB : 1) : (int)__umulhi((unsigned)e, w.nbmagic);
+            const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
             const float4 s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
             if (NB) {
 #pragma unroll
@@ -606,12 +614,13 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
     const int *lst = reinterpret_cast<const int *>(smem) + w.lst;
     bool ov = false;
     int namb = 0, ai = 0, aj = 0;
+#pragma unroll 1
     for (int p0 = 0; p0 < nitems; p0 += T) {
         const int p = p0 + w.lane;
         bool near = false;
         int packed = 0;
         if (p < nitems) {
-            const int d1 = (int)__umulhi((unsigned)p, w.ncmagic); // offset - 1
+            const int d1 = div_nc(w, p); // offset - 1
             const int ci = p - d1 * nc, d = d1 + 1;
             int cj = ci + d;
             if (cj >= nc) cj -= nc;
@@ -622,11 +631,13 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
             }
         }
         const int items = near_list<T>(w, near, packed) * nb;
+#pragma unroll 1
         for (int e = w.lane; e < items; e += T) {
-            const int pi = (int)__umulhi((unsigned)e, w.nbmagic);
+            const int pi = div_nb(w, e);
             const int pk = lst[pi];
             const int bi = (pk >> 16) * nb + (e - pi * nb), cj0 = (pk & 0xffff) * nb;
             const float4 s = SM4[g4 + bi];
+#pragma unroll 1
             for (int b = 0; b < nb; ++b) {
                 const float4 t = SM4[g4 + cj0 + b];
                 const float r2 = r2_f32(f, s.x - t.x, s.y - t.y, s.z - t.z);
@@ -643,6 +654,7 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
     if (with_intra && w.npc > 0) { // same-chain pairs further apart than nexclude (shear / stretch, MCNS.py:198,247)
         const uchar2 *tab = W_ITAB(w);
         const int total = nc * w.npc;
+#pragma unroll 1
         for (int e = w.lane; e < total; e += T) {
             const int c = e / w.npc;
             const uchar2 jb = tab[e - c * w.npc];
@@ -740,8 +752,9 @@ __device__ __noinline__ void follow_cell(WCtx w, int src, int dst, int dst4, int
     double Hio[9], Hn[9], Hin[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { Hio[k] = smem[hi_old + k]; Hn[k] = smem[h_new + k]; Hin[k] = smem[hi_new + k]; }
+#pragma unroll 1
     for (int i = w.lane; i < w.N; i += T) {
-        const int a = src + 3 * ((i / w.nb) * w.nb);
+        const int a = src + 3 * (div_nb(w, i) * w.nb);
         const double ax = smem[a], ay = smem[a + 1], az = smem[a + 2];
         double f0, f1, f2, n0, n1, n2;
         vecmat(ax, ay, az, Hio, f0, f1, f2);
@@ -755,7 +768,9 @@ __device__ __noinline__ void follow_cell(WCtx w, int src, int dst, int dst4, int
 template <int T> __device__ __forceinline__ void commit_trial(const WCtx &w)
 {
     const int p = W_P(w), tp = W_TP(w), f4 = W_F4(w), g4 = W_G4(w), sh = W_SH(w), sf = W_SF(w);
+#pragma unroll 1
     for (int i = w.lane; i < 3 * w.N; i += T) smem[p + i] = smem[tp + i];
+#pragma unroll 1
     for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = SM4[g4 + i];
     if (w.lane < 18) smem[sh + w.lane] = smem[sh + 18 + w.lane];
     if (w.lane < 9) SMF[sf + w.lane] = SMF[sf + SF_TRIAL + w.lane];
@@ -882,6 +897,7 @@ __device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, con
 {
     const double *r = gR + (size_t)wi * w.N * 3;
     const int p = W_P(w), sh = W_SH(w);
+#pragma unroll 1
     for (int i = w.lane; i < 3 * w.N; i += T) smem[p + i] = r[i];
     double H[9], Hi[9];
 #pragma unroll
@@ -894,8 +910,10 @@ __device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, con
     gsync<T>();
     if (shadows) {
         const int f4 = W_F4(w);
+#pragma unroll 1
         for (int i = w.lane; i < w.N; i += T) SM4[f4 + i] = shadow_of(smem[p + 3 * i], smem[p + 3 * i + 1], smem[p + 3 * i + 2], smem + sh + 9);
         if (w.nb > 1)
+#pragma unroll 1
             for (int c = w.lane; c < w.nc; c += T) SMF[w.rad + c] = chain_radius(p + 3 * c * w.nb, w.nb);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
@@ -907,6 +925,7 @@ __device__ __forceinline__ void store_walker(const WCtx &w, double *gH, double *
 {
     double *r = gR + (size_t)wi * w.N * 3;
     const int p = W_P(w), sh = W_SH(w);
+#pragma unroll 1
     for (int i = w.lane; i < 3 * w.N; i += T) r[i] = smem[p + i];
     if (w.lane < 9) gH[(size_t)wi * 9 + w.lane] = smem[sh + w.lane];
 }
