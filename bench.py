@@ -33,6 +33,7 @@ WORKLOADS = {
     "C2": (64, 1, [1, 192, 0, 0, 3, 3], 1024, 132.0),
     "C3": (16, 6, [3, 48, 32, 0, 3, 3], 1024, 922.0),
     "C4": (32, 12, [3, 32, 32, 16, 3, 3], 512, 11235.0),
+    "C5": (128, 6, [1, 384, 256, 384, 3, 3], 256, 6528.0),
 }
 FLOP_PER_PAIR = 45.0
 WALKLENGTH = 40
@@ -279,6 +280,14 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         return float(t.item())
 
+    # which kernel hans_mc_run_batch_ws dispatches this shape to; the events
+    # bracket the proposal generator + the walk kernel of one launch
+    from hans_b200 import _lib
+    import ctypes as C
+    win = _lib.lib.hans_default_window(C.byref(pool.cfg)) if args.tpw == 0 else (args.tpw if args.tpw < 32 else 0)
+    tpw_coop = args.tpw if args.tpw >= 32 else _lib.lib.hans_default_threads_per_walker(C.byref(pool.cfg))
+    walk_kernel_name = (f"hb::walk_lean_kernel<NB={nbeads},W={win}> (one warp per walker)" if win
+                        else f"hb::walk_kernel<T={tpw_coop}> (one CTA per walker)") + " + hb::gen_kernel"
     # FP32 FFMA issue peak of this GPU (roofline denominator; MEASURED_PEAKS.json has no FP32 figure)
     ffma_peak = engine.ffma_peak_tflops()
 
@@ -315,6 +324,36 @@ def run_b200(args):
     d2h_bytes = hvol.numel() * 8 + 8
     ns.flush()
 
+    # ---- dense regime: compress by nested sampling itself, then time the same step ---
+    dense = None
+    if args.dense_eta > 0:
+        rr, dd = 0.5, 0.4   # fused-sphere chain volume, Intersecting_Sphere_Notes.ipynb
+        vchain = 4 / 3 * np.pi * rr ** 3 + np.pi * (nbeads - 1) * (16 * rr ** 3 - (dd - 2 * rr) ** 2 * (dd + 4 * rr)) / 12
+        interval = max(nw * world // 2, 1)  # mpihans.py:248: step sizes adapted every K/2 iterations
+        it, eta = 0, 0.0
+        while it < args.dense_max_iters:
+            ns.run(interval)
+            ns.adjust_mc_steps()
+            ns.flush()
+            it += interval
+            eta = nchains * vchain / ns.volume_limit()
+            if eta >= args.dense_eta:
+                break
+        pool.pair_tests.zero_()
+        ns.walk_counters = True
+        ns.run(3)
+        att = ns.att.sum(0).double().cpu().numpy(); accd = ns.acc.sum(0).double().cpu().numpy()
+        ns.walk_counters = False
+        pool.pair_tests.zero_()
+        dsteps = max(args.steps // 2, 1)
+        ms_d = max_over_ranks(timed_region(dsteps))
+        dense = {"value": dsteps * moves_per_step / (ms_d * 1e-3), "unit": "moves/s", "steps": dsteps,
+                 "ms_per_step": ms_d / dsteps, "packing_fraction": eta, "compression_iterations": it,
+                 "acceptance_by_type": [round(float(a / max(b, 1.0)), 3) for a, b in zip(accd, att)],
+                 "step_sizes": {k: round(v, 5) for k, v in ns.steps().items()},
+                 "executed_pair_tests_per_move": int(pool.pair_tests.item()) / (dsteps * nw * WALKLENGTH * mps)}
+        ns.flush()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -332,7 +371,7 @@ def run_b200(args):
     if rank == 0:
         pairs_per_launch = apm * nw * WALKLENGTH * mps
         achieved = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
-        achieved_exec = FLOP_PER_PAIR * (executed_pairs / world) / (kernel_ms * 1e-3) / 1e12
+        achieved_exec = FLOP_PER_PAIR * executed_pairs / (kernel_ms * 1e-3) / 1e12  # (this rank's counter)
         line = {
             "metric": "mc_move_attempts_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -350,13 +389,14 @@ def run_b200(args):
             "clocks": clk,
             "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": achieved / ffma_peak, "traffic": None,
-                         "kernel": "hb::walk_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "kernel": walk_kernel_name, "kernel_ms_per_launch": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (ms / args.steps),
                          "algorithmic_pair_tests_per_launch": pairs_per_launch, "flop_per_pair_test": FLOP_PER_PAIR,
-                         "executed_pair_tests_per_launch": executed_pairs / world, "achieved_executed": achieved_exec,
+                         "executed_pair_tests_per_launch": executed_pairs, "achieved_executed": achieved_exec,
                          "peak_source": "FFMA issue-rate probe (hans_ffma_peak) run in this process; "
                                         "MEASURED_PEAKS.json holds no FP32 figure"},
             "cpu_baseline": cpu,
+            "dense_regime": dense,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -375,6 +415,9 @@ def main():
     ap.add_argument("--initial-walk", type=int, default=100, help="unconstrained sweeps after growth (reference: 1000)")
     ap.add_argument("--tpw", type=int, default=0, help="threads per walker (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dense-eta", type=float, default=0.0,
+                    help="also time the step after compressing (by NS + step adaptation) to this packing fraction; 0 = skip")
+    ap.add_argument("--dense-max-iters", type=int, default=8000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-shaped", action="store_true", help="also time the MC_run-shaped Python loop (BASELINE.md variant i)")
     args = ap.parse_args()

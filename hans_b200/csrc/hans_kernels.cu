@@ -276,12 +276,18 @@ static int pick_T(const hans_cfg *c, int T)
 
 static int spec_grid(int n) { const int cap = sm_count() * 32; return n < cap ? n : cap; }
 
-// beads-per-chain counts the lean warp-per-walker kernel (hans_lean.cuh) is instantiated for
+// Shapes the lean warp-per-walker kernel (hans_lean.cuh) runs: beads-per-chain counts it is
+// instantiated for; single spheres up to 128 beads (every pair is tested), chains of any size that
+// fits shared memory (the chain-level pruning leaves a warp's worth of pair tests per move).
 static bool lean_applies(const hans_cfg *c)
 {
     const int nb = c->nbeads, N = c->nchains * c->nbeads;
-    if (N > 128) return false;
-    return nb == 1 || nb == 2 || nb == 4 || nb == 6 || nb == 8 || nb == 12;
+    if (!(nb == 1 || nb == 2 || nb == 4 || nb == 6 || nb == 8 || nb == 12)) return false;
+    if (N <= 128) return true;
+    // measured (profiles/r01_*): 32 chains x 12 beads 150 vs 112 M moves/s (one CTA of 128 threads per walker);
+    // 128 chains x 6 beads 99 vs 137 -- beyond two waves of chain spheres per move the CTA wins
+    if (nb == 1 || c->nchains > 64) return false;
+    return walker_smem_bytes(N, nb, 32) + cta_extra_bytes(nb, c->nexclude) <= 200 * 1024;
 }
 
 #define DISPATCH_NB(NB, ...)                                 \
@@ -319,6 +325,7 @@ static int pick_W(const hans_cfg *c, int tpw)
 {
     if (tpw >= 32 || !lean_applies(c)) return -1;
     if (tpw == 0) return hans_default_window(c);
+    if (tpw == 8 && c->nchains * c->nbeads > 128) return -1; // the windows' bit words cover 4 x 32 beads
     return (tpw == 1 || tpw == 8) ? tpw : -1;
 }
 
@@ -361,8 +368,7 @@ int hans_default_threads_per_walker(const hans_cfg *cfg)
     const int N = cfg->nchains * cfg->nbeads;
     if (N <= 128) return 32;
     if (N <= 256) return 64;
-    if (N <= 512) return 128;
-    return 256;
+    return 128; // (256 threads per walker measured slower at every BASELINE shape: barriers dominate)
 }
 
 int hans_default_window(const hans_cfg *cfg)

@@ -70,7 +70,7 @@ def test_host_side_entry_points_and_validation():
     assert L.hans_walker_smem_bytes(C.byref(cfg)) == want
     assert L.hans_default_threads_per_walker(C.byref(cfg)) == 32
     big = _lib.make_cfg(128, 6, [1, 384, 256, 384, 3, 3])
-    assert L.hans_default_threads_per_walker(C.byref(big)) == 256
+    assert L.hans_default_threads_per_walker(C.byref(big)) == 128
     # argument errors are reported as codes + text, never by exiting, and need no GPU
     assert L.hans_mc_run_batch(None, None, None, None, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 0, None) == -1
     assert b"cfg" in L.hans_last_error()

@@ -149,6 +149,22 @@ def test_replay_dense_rejections(eng, oracle, tpw):
     assert (dec["reason"] == 1).mean() > 0.2
 
 
+@pytest.mark.parametrize("shape,tpw,density", [("C1", 0, 0.15), ("C1", 64, 0.15), ("C1", 0, 0.45), ("C1", 32, 0.45), ("C1", 128, 0.3), ("C1", 8, 0.45),
+                                                ("C4s", 0, 0.4), ("C4s", 64, 0.4), ("dimer", 0, 0.5), ("tiny", 0, 0.5)])
+def test_replay_dense_chains(eng, oracle, shape, tpw, density):
+    """Chain systems compressed until the chains' bounding spheres touch many neighbours and the cell is only a
+    few diameters wide: the chain-level pruning keeps most neighbours (or, once the bounding distance exceeds half
+    the cell width, all of them) and decisions must still be the checker's, bit for bit."""
+    nchains, nbeads, _ = SHAPES[shape]
+    SHAPES["_tmp"] = (nchains, nbeads, [2, 6, 6, 3 if nbeads >= 4 else 0, 2, 2])
+    try:
+        props, dec = _replay_case(eng, oracle, "_tmp", tpw, nwalkers=6, nmoves=500, dense=density, dr_max=0.25, dt_max=0.3,
+                                  dh_max=0.3, dv_max=2.0, dshear=0.1, dstretch=0.05)
+    finally:
+        del SHAPES["_tmp"]
+    assert (dec["reason"] == 1).mean() > 0.02 and dec["accepted"].mean() > 0.05
+
+
 @pytest.mark.parametrize("shape,tpw", [("C2", 8), ("C1", 8), ("C4s", 8), ("dimer", 8)])
 def test_replay_windows_only_chain_moves(eng, oracle, shape, tpw):
     """No box moves at all: every window of the speculative path is full, and with small steps most
