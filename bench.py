@@ -329,16 +329,31 @@ def run_b200(args):
     if args.dense_eta > 0:
         rr, dd = 0.5, 0.4   # fused-sphere chain volume, Intersecting_Sphere_Notes.ipynb
         vchain = 4 / 3 * np.pi * rr ** 3 + np.pi * (nbeads - 1) * (16 * rr ** 3 - (dd - 2 * rr) ** 2 * (dd + 4 * rr)) / 12
-        interval = max(nw * world // 2, 1)  # mpihans.py:248: step sizes adapted every K/2 iterations
+        # isotropic shrink steps through alkane_change_box, each kept only where no overlap appears,
+        # with short constant-volume walks in between (the procedure of tests/common.py:compress, on
+        # the device); nested sampling itself compresses by only 1/(K N) in ln V per iteration
+        all_ids = torch.arange(nw, dtype=torch.int32, device=dev)
+        relax = pool.cfg_with([0.0] + [float(x) for x in mr[1:]])
         it, eta = 0, 0.0
         while it < args.dense_max_iters:
-            ns.run(interval)
-            ns.adjust_mc_steps()
-            ns.flush()
-            it += interval
-            eta = nchains * vchain / ns.volume_limit()
+            Hb, Rb = pool.H.clone(), pool.R.clone()
+            pool.change_box(all_ids, ((args.dense_shrink - 1.0) * pool.H).cpu().numpy())
+            bad = pool.check_overlap().bool()
+            pool.H[bad] = Hb[bad]
+            pool.R[bad] = Rb[bad]
+            pool.refresh_volumes()
+            pool.mc_run(2, counters=False, cfg=relax, count_pairs=False)
+            it += 1
+            if it % 10 == 0:
+                pool.cfg.dr_max = max(0.5 * pool.cfg.dr_max, 0.05) if bad.float().mean().item() > 0.5 else pool.cfg.dr_max
+                relax = pool.cfg_with([0.0] + [float(x) for x in mr[1:]])
+            eta = nchains * vchain / float(pool.vol.median().item())
             if eta >= args.dense_eta:
                 break
+        for _ in range(4):  # adjust_mc_steps (MCNS.py:657-717) under the current ceiling
+            ns.run(2)
+            ns.adjust_mc_steps()
+        ns.flush()
         pool.pair_tests.zero_()
         ns.walk_counters = True
         ns.run(3)
@@ -348,7 +363,7 @@ def run_b200(args):
         dsteps = max(args.steps // 2, 1)
         ms_d = max_over_ranks(timed_region(dsteps))
         dense = {"value": dsteps * moves_per_step / (ms_d * 1e-3), "unit": "moves/s", "steps": dsteps,
-                 "ms_per_step": ms_d / dsteps, "packing_fraction": eta, "compression_iterations": it,
+                 "ms_per_step": ms_d / dsteps, "packing_fraction": eta, "compression_rounds": it,
                  "acceptance_by_type": [round(float(a / max(b, 1.0)), 3) for a, b in zip(accd, att)],
                  "step_sizes": {k: round(v, 5) for k, v in ns.steps().items()},
                  "executed_pair_tests_per_move": int(pool.pair_tests.item()) / (dsteps * nw * WALKLENGTH * mps)}
@@ -417,9 +432,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dense-eta", type=float, default=0.0,
                     help="also time the step after compressing (by NS + step adaptation) to this packing fraction; 0 = skip")
-    ap.add_argument("--dense-max-iters", type=int, default=8000)
+    ap.add_argument("--dense-max-iters", type=int, default=600)
+    ap.add_argument("--dense-shrink", type=float, default=0.985)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--cpu-shaped", action="store_true", help="also time the MC_run-shaped Python loop (BASELINE.md variant i)")
+    ap.add_argument("--cpu-shaped", action="store_true", default=True,
+                    help="also time the MC_run-shaped Python loop (BASELINE.md variant i); on by default")
+    ap.add_argument("--no-cpu-shaped", dest="cpu_shaped", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
