@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhans_b200.so")
+# HANS_B200_LIB: another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("HANS_B200_LIB") or os.path.join(_HERE, "libhans_b200.so")
 
 VOL, TRANS, ROT, DIH, SHEAR, STRETCH = range(6)
 MODE_FUSED, MODE_PROPOSE = 0, 1

@@ -274,8 +274,11 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
 }
 
 // W = 1: strictly one move at a time; W = 4 / 8: speculative windows of up to W moves
+#ifndef HANS_LEAN_MIN_CTAS
+#define HANS_LEAN_MIN_CTAS 1
+#endif
 template <int NB, int W, bool REPLAY>
-__global__ void __launch_bounds__(32) walk_lean_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(32, HANS_LEAN_MIN_CTAS) walk_lean_kernel(const WalkArgs a)
 {
     constexpr int T = 32;
     const WCtx w = setup_ctx_g<32, 1>(a.cfg, W > 1 ? W : 0);

@@ -9,6 +9,8 @@ SHAPES = {
     "C2": (64, 1, [1, 192, 0, 0, 3, 3]),
     "C4s": (8, 12, [3, 32, 32, 16, 3, 3]),   # C4's chain length, fewer chains
     "dimer": (32, 2, [1, 96, 64, 0, 3, 3]),  # the committed input.txt shape
+    "C4": (32, 12, [3, 32, 32, 16, 3, 3]),   # BASELINE configs[3], full walker size (384 beads)
+    "C5": (128, 6, [1, 384, 256, 384, 3, 3]),  # BASELINE configs[4], full walker size (768 beads)
     "tiny": (6, 2, [1, 18, 12, 0, 3, 3]),    # fewer beads than lanes: several lanes share a bead row in box moves
     "tiny1": (5, 1, [1, 15, 0, 0, 3, 3]),
 }

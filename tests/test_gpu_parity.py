@@ -204,15 +204,16 @@ def test_replay_invalid_and_edge(eng, oracle):
                                                ("C4s", 32, 3), ("C4s", 256, 2), ("dimer", 32, 5),
                                                ("C1", 0, 6), ("C1", 1, 6), ("C1", 8, 4), ("C2", 0, 10), ("C2", 8, 6),
                                                ("C2", 1, 6), ("C4s", 0, 3), ("C4s", 8, 3), ("dimer", 0, 5), ("dimer", 8, 5),
-                                               ("tiny", 0, 12), ("tiny", 32, 12), ("tiny1", 0, 12), ("tiny1", 64, 12)])
+                                               ("tiny", 0, 12), ("tiny", 32, 12), ("tiny1", 0, 12), ("tiny1", 64, 12),
+                                               ("C4", 0, 1), ("C4", 128, 1), ("C5", 0, 1), ("C5", 128, 1), ("C5", 256, 1)])
 def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
-    nw = 10
+    nw = 10 if shape not in ("C4", "C5") else 7
     cfg, H, R, k = make_walkers(shape, nw, seed=31)
     seed = 424242
     limit = float(np.median([oracle.volume(H[w]) for w in range(nw)]))  # ceiling bites for half
     pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=tpw)
     pool.gid_base = 1000
-    ids = [7, 2, 9, 0, 4]
+    ids = [7, 2, 9, 0, 4] if nw == 10 else [5, 2, 6, 0]
     att, acc = pool.mc_run(sweeps, ids=ids, volume_limit=limit)
     att2, acc2 = pool.mc_run(1, ids=ids, volume_limit=limit)  # continues the per-walker counters
     ctrs = np.zeros(nw, dtype=np.uint64)

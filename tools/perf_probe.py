@@ -8,6 +8,9 @@ CASES = {
     "C2": (64, 1, [1, 192, 0, 0, 3, 3], 1024),
     "C3_1024": (16, 6, [3, 48, 32, 0, 3, 3], 1024),
     "C3_4096": (16, 6, [3, 48, 32, 0, 3, 3], 4096),
+    "C3_8192": (16, 6, [3, 48, 32, 0, 3, 3], 8192),
+    "C2_4096": (64, 1, [1, 192, 0, 0, 3, 3], 4096),
+    "C2_8192": (64, 1, [1, 192, 0, 0, 3, 3], 8192),
     "C4_512": (32, 12, [3, 32, 32, 16, 3, 3], 512),
     "C5_256": (128, 6, [1, 384, 256, 384, 3, 3], 256),
 }
