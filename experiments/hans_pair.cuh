@@ -1,3 +1,7 @@
+// ARCHIVED EXPERIMENT -- not part of the library build.  Measured slower than hans_lean.cuh (DESIGN.md section 3,
+// profiles/r01_ncu_c2_two_warps_per_walker_experiment.txt).  To rebuild it, WCtx needs redirectable trial-chain
+// fields (`cn`, `c4`, used by W_CN / W_C4) and hans_kernels.cu a launch_pair dispatch; see the git history.
+//
 // hans_pair.cuh -- MC_run with TWO WARPS per walker: two consecutive single-chain moves evaluated at
 // the same time, settled in order.
 //
