@@ -65,25 +65,25 @@ __device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRe
     const double x = smem[P] + p->p[0], y = smem[P + 1] + p->p[1], z = smem[P + 2] + p->p[2];
     const float4 cs = shadow_of(x, y, z, cr.Hi);
     const Filt &f = cr.f;
-    bool ov = false, amb = false;
+    float rmin = 3.0e38f; // smallest float32 r^2 over the beads this lane owns
 #pragma unroll 2
     for (int j = w.lane; j < N; j += 32) {
         const float4 s = SM4[f4 + j];
         const float r2 = r2_f32(f, s.x - cs.x, s.y - cs.y, s.z - cs.z);
-        const bool other = j != ichain;
-        ov |= other && (r2 < f.lo);
-        amb |= other && !(r2 > f.hi);
+        rmin = (j != ichain) ? fminf(rmin, r2) : rmin;
     }
     pairs += (unsigned)((N - 1 - w.lane + 32) >> 5);
-    const unsigned code = __reduce_or_sync(FULL, (ov ? 2u : 0u) | (amb ? 1u : 0u));
-    bool overlap = (code & 2u) != 0u;
-    if (code == 1u) { // nothing overlaps for certain, but a pair is inside the band: float64 decides
+    // one REDUX for the vote: as integers all negative floats sort below all positive ones, and a (tiny,
+    // rounding) negative r^2 is "< lo" like any other certain overlap
+    const float m = __int_as_float(__reduce_min_sync(FULL, __float_as_int(rmin)));
+    bool overlap = m < f.lo;
+    if (!overlap && !(m > f.hi)) { // nothing overlaps for certain, but a pair is inside the band: float64 decides
         if (w.lane == 0) {
             const int cn = W_CN(w);
             smem[cn] = x; smem[cn + 1] = y; smem[cn + 2] = z;
         }
         __syncwarp();
-        overlap = lean_recheck(w, ichain, 0, amb, false);
+        overlap = lean_recheck(w, ichain, 0, true, false);
     }
     if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
         if (w.lane == 0) {

@@ -71,6 +71,17 @@ def test_host_side_entry_points_and_validation():
     assert L.hans_default_threads_per_walker(C.byref(cfg)) == 32
     big = _lib.make_cfg(128, 6, [1, 384, 256, 384, 3, 3])
     assert L.hans_default_threads_per_walker(C.byref(big)) == 128
+    # kernel selection per shape: warp-per-walker kernel for small walkers and for chain systems
+    # of up to 64 chains, the cooperative one otherwise
+    assert L.hans_default_window(C.byref(cfg)) == 1
+    assert L.hans_default_window(C.byref(_lib.make_cfg(64, 1, [1, 192, 0, 0, 3, 3]))) == 1
+    assert L.hans_default_window(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 1
+    assert L.hans_default_window(C.byref(big)) == 0                                        # 128 chains: one CTA per walker
+    assert L.hans_default_window(C.byref(_lib.make_cfg(16, 5, [1, 1, 1, 1, 1, 1]))) == 0   # nbeads = 5 is not instantiated
+    assert L.hans_default_window(C.byref(_lib.make_cfg(200, 1, [1, 1, 0, 0, 1, 1]))) == 0  # 200 spheres
+    assert L.hans_mc_run_batch_ws(None, None, None, None, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 0, None, 0, None) == -1
+    assert L.hans_gen_proposals(C.byref(cfg), None, None, 1, 1, 0, 0, None, None) == -1
+    assert b"required" in L.hans_last_error()
     # argument errors are reported as codes + text, never by exiting, and need no GPU
     assert L.hans_mc_run_batch(None, None, None, None, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 0, None) == -1
     assert b"cfg" in L.hans_last_error()
