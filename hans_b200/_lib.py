@@ -62,7 +62,8 @@ EXPORTS = [
     "hans_mc_run_batch_ws", "hans_gen_proposals",
     "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
-    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_diag_counters", "hans_ffma_peak",
+    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_order_params", "hans_diag_counters",
+    "hans_ffma_peak",
 ]
 
 
@@ -119,6 +120,7 @@ def _load():
     L.hans_clone.argtypes = [cp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     L.hans_ns_pack.argtypes = [C.POINTER(NsArgs), vp]
     L.hans_ns_resolve.argtypes = [C.POINTER(NsArgs), vp]
+    L.hans_order_params.argtypes = [cp, vp, vp, i32, vp, vp, vp]
     L.hans_diag_counters.argtypes = [vp, i32]
     L.hans_ffma_peak.argtypes = [i32, C.POINTER(f64), vp]
     for name in EXPORTS:

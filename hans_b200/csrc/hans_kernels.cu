@@ -195,6 +195,80 @@ __global__ void ns_resolve_kernel(const hans_ns_args a)
     if (threadIdx.x == 0) *a.d_iter = it + 1;
 }
 
+// Order parameters of n configurations (nematic.py:83-137 nematic P2; nematic.py:30-55 translational), one warp
+// per configuration, lanes over chains.
+//   P2    largest eigenvalue of Q = mean_chains (3 u u^T - I) / 2, u = unit minimum-image end-to-end vector
+//         (bead 0 -> bead nbeads-1; nematic.py:112-121).  Single beads have no director: P2 = 0.
+//   trans |sum_chains exp(2 pi i (s_x + s_y + s_z))| / nchains over the fractional "centres" the reference uses:
+//         the mean of beads 0 .. nbeads-2 (the slice a0:a1 of nematic.py:66-72 leaves the last bead out), or the
+//         bead itself for nbeads = 1; every bead wrapped into the cell first, as ase's get_scaled_positions does.
+__global__ void order_kernel(const hans_cfg cfg, const double *gH, const double *gR, int n, double *p2, double *trans)
+{
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n) return;
+    const int nb = cfg.nbeads, nc = cfg.nchains;
+    double H[9], Hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = gH[(size_t)wid * 9 + k];
+    hinv(H, Hi);
+    const double *R = gR + (size_t)wid * nb * nc * 3;
+    double q[6] = {0, 0, 0, 0, 0, 0}, re = 0.0, im = 0.0;
+    for (int c = lane; c < nc; c += 32) {
+        const double *r0 = R + (size_t)c * nb * 3;
+        if (nb > 1) {
+            const double *r1 = r0 + (size_t)(nb - 1) * 3;
+            double s0, s1, s2, ux, uy, uz;
+            vecmat(r1[0] - r0[0], r1[1] - r0[1], r1[2] - r0[2], Hi, s0, s1, s2);
+            s0 -= hd_rint(s0); s1 -= hd_rint(s1); s2 -= hd_rint(s2);
+            vecmat(s0, s1, s2, H, ux, uy, uz);
+            const double inv = 1.0 / sqrt((ux * ux + uy * uy) + uz * uz);
+            ux *= inv; uy *= inv; uz *= inv;
+            q[0] += 1.5 * ux * ux - 0.5; q[1] += 1.5 * uy * uy - 0.5; q[2] += 1.5 * uz * uz - 0.5;
+            q[3] += 1.5 * ux * uy; q[4] += 1.5 * ux * uz; q[5] += 1.5 * uy * uz;
+        }
+        // ase's get_scaled_positions() wraps every atom into [0, 1) before the mean is taken (nematic.py:66-72)
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+        const int m = nb > 1 ? nb - 1 : 1;
+        for (int b = 0; b < m; ++b) {
+            double g0, g1, g2;
+            vecmat(r0[3 * b], r0[3 * b + 1], r0[3 * b + 2], Hi, g0, g1, g2);
+            f0 += g0 - floor(g0); f1 += g1 - floor(g1); f2 += g2 - floor(g2);
+        }
+        f0 /= (double)m; f1 /= (double)m; f2 /= (double)m;
+        double sn, cs;
+        sincos(HD_TWO_PI * ((f0 + f1) + f2), &sn, &cs);
+        re += cs; im += sn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] += __shfl_down_sync(FULL, q[k], o);
+        re += __shfl_down_sync(FULL, re, o);
+        im += __shfl_down_sync(FULL, im, o);
+    }
+    if (lane != 0) return;
+    if (trans) trans[wid] = sqrt(re * re + im * im) / (double)nc;
+    if (p2) {
+        double e = 0.0;
+        if (nb > 1) {
+            const double a11 = q[0] / nc, a22 = q[1] / nc, a33 = q[2] / nc, a12 = q[3] / nc, a13 = q[4] / nc, a23 = q[5] / nc;
+            const double p1 = (a12 * a12 + a13 * a13) + a23 * a23;
+            const double tq = ((a11 + a22) + a33) / 3.0;
+            const double pp = ((a11 - tq) * (a11 - tq) + (a22 - tq) * (a22 - tq)) + ((a33 - tq) * (a33 - tq) + 2.0 * p1);
+            const double pr = sqrt(pp / 6.0);
+            if (pr < 1e-300) e = tq;
+            else {
+                const double b11 = (a11 - tq) / pr, b22 = (a22 - tq) / pr, b33 = (a33 - tq) / pr;
+                const double b12 = a12 / pr, b13 = a13 / pr, b23 = a23 / pr;
+                double r = 0.5 * ((b11 * (b22 * b33 - b23 * b23) - b12 * (b12 * b33 - b23 * b13)) + b13 * (b12 * b23 - b22 * b13));
+                r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+                e = tq + 2.0 * pr * cos(acos(r) / 3.0); // largest eigenvalue of a symmetric 3x3 matrix
+            }
+        }
+        p2[wid] = e;
+    }
+}
+
 // FP32 FFMA issue-rate probe (roofline denominator)
 __global__ void ffma_kernel(int iters, float *sink)
 {
@@ -633,6 +707,19 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream)
     int rc = check_ns(a);
     if (rc) return rc;
     ns_resolve_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_order_params(const hans_cfg *cfg, const double *d_H, const double *d_R, int n, double *d_p2, double *d_trans,
+                      void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_H || !d_R) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 0) return fail(HANS_EINVAL, "negative count");
+    if (n == 0) return HANS_OK;
+    order_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*cfg, d_H, d_R, n, d_p2, d_trans);
     CK(cudaGetLastError());
     return HANS_OK;
 }

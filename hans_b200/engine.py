@@ -137,6 +137,15 @@ class WalkerPool:
                                   d.data_ptr(), _stream()))
         self.launches += 1
 
+    def order_parameters(self):
+        """(P2 nematic, translational) order parameter of every walker (nematic.py:30-137), device tensors."""
+        f64 = dict(dtype=torch.float64, device=self.device)
+        p2, tr = torch.empty(self.nwalkers, **f64), torch.empty(self.nwalkers, **f64)
+        check(lib.hans_order_params(C.byref(self.cfg), self.H.data_ptr(), self.R.data_ptr(), self.nwalkers,
+                                    p2.data_ptr(), tr.data_ptr(), _stream()))
+        self.launches += 1
+        return p2, tr
+
     # ---- initial configurations ---------------------------------------------------------------
     def set_initial_cells(self, max_vol_per_atom: float = 15.0) -> None:
         """create_initial_configs, MCNS.py:628-631."""

@@ -247,6 +247,15 @@ int hans_ns_pack(const hans_ns_args *a, void *stream);
  * walker list (mpihans.py:236-239), iteration counter += 1 */
 int hans_ns_resolve(const hans_ns_args *a, void *stream);
 
+/* ---- order parameters (the reference's offline nematic.py) ---------------------------
+ * For n configurations: d_p2[k] = nematic order parameter P2, the largest eigenvalue of
+ * Q = mean over chains of (3 u u^T - I)/2 with u the unit minimum-image end-to-end vector
+ * (nematic.py:83-137; 0 for nbeads = 1); d_trans[k] = the translational order parameter
+ * |sum_chains exp(2 pi i (s_x+s_y+s_z))| / nchains over the fractional chain centres as the
+ * reference takes them (mean of beads 0..nbeads-2, nematic.py:30-72).  Either output may be NULL. */
+int hans_order_params(const hans_cfg *cfg, const double *d_H, const double *d_R, int n, double *d_p2,
+                      double *d_trans, void *stream);
+
 /* Diagnostics (synchronises): out4[0] = trial chains re-tested in float64 because a pair fell into
  * the float32 filter's band, out4[1] = float64 all-pairs passes of box moves; reset != 0 zeroes them. */
 int hans_diag_counters(uint64_t *out4, int reset);

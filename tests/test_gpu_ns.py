@@ -214,3 +214,50 @@ def test_full_size_invariants(eng, nchains, nbeads, mr, nw):
         b = np.diff(Ra.reshape(nw, nchains, nbeads, 3), axis=2)
         assert np.allclose(np.linalg.norm(b, axis=3), 0.4, atol=1e-9)                # rigid bonds
     assert (pa.ctr.cpu().numpy() == sweeps * mps).all()
+
+
+# ---- order parameters on the device vs the numpy restatement of nematic.py ------------------------
+@pytest.mark.parametrize("nchains,nbeads,mr", [(16, 6, [3, 48, 32, 0, 3, 3]), (64, 1, [1, 192, 0, 0, 3, 3]),
+                                                (8, 12, [3, 32, 32, 16, 3, 3]), (40, 2, [1, 96, 64, 0, 3, 3])])
+def test_order_parameters_match_numpy(eng, nchains, nbeads, mr):
+    from oracle import order_params as op
+    pool = _pool(eng, 37, nchains, nbeads, mr, seed=11)
+    pool.mc_run(30, counters=False)                  # cells sheared / stretched, chains rotated
+    p2, tr = (t.cpu().numpy() for t in pool.order_parameters())
+    H, R = pool.get_state()
+    want_p2 = op.nematic_order_param(H, R, nbeads, nchains)
+    want_tr = op.trans_order_param(H, R, nbeads, nchains)
+    # tolerance: float64 sums in a different order, closed-form eigenvalue vs LAPACK
+    assert np.allclose(p2, want_p2, rtol=0, atol=1e-10)
+    assert np.allclose(tr, want_tr, rtol=0, atol=1e-10)
+    if nbeads > 1:
+        assert (p2 > -0.5 - 1e-12).all() and (p2 <= 1 + 1e-12).all() and p2.std() > 0
+    # a perfectly aligned configuration has P2 = 1
+    Ra = R.copy()
+    for c in range(nchains):
+        for b in range(nbeads):
+            Ra[:, c * nbeads + b] = Ra[:, c * nbeads] + 0.1 * b * np.array([0.0, 0.6, 0.8])
+    if nbeads > 1:
+        pool.set_state(H, Ra)
+        assert np.allclose(pool.order_parameters()[0].cpu().numpy(), 1.0, atol=1e-12)
+
+
+def test_order_parameters_from_trajectory_file(eng, tmp_path):
+    """hans_b200.nematic mirrors nematic.py on a traj.extxyz written by the driver's own writer (wrapped atoms)."""
+    from hans_b200 import NSio, nematic
+    from hans_b200.atoms import read_extxyz
+    from oracle import order_params as op
+    pool = _pool(eng, 5, 16, 6, [3, 48, 32, 0, 3, 3], seed=3)
+    pool.mc_run(10, counters=False)
+    H, R = pool.get_state()
+    fn = str(tmp_path / "traj.extxyz")
+    for w in range(5):
+        NSio.write_to_extxyz(H[w], R[w], filename=fn)
+    frames = read_extxyz(fn, index=":")
+    assert len(frames) == 5
+    cells = [np.asarray(f.get_cell()) for f in frames]
+    pos = [np.asarray(f.get_positions()) for f in frames]
+    assert np.allclose(nematic.nematic_order_param(frames, 6, 16), op.nematic_order_param(cells, pos, 6, 16), atol=1e-10)
+    assert np.allclose(nematic.trans_order_param(frames, 6, 16), op.trans_order_param(cells, pos, 6, 16), atol=1e-10)
+    # wrapping atoms does not change the nematic order (minimum-image end-to-end vectors)
+    assert np.allclose(nematic.nematic_order_param(frames, 6, 16), pool.order_parameters()[0].cpu().numpy(), atol=1e-9)

@@ -306,3 +306,29 @@ def test_oracle_ns_reproduces_golden_curve(oracle):
     rr, d, n = 0.5, 0.4, 4
     vchain = 4 / 3 * np.pi * rr ** 3 + np.pi * (n - 1) * (16 * rr ** 3 - (d - 2 * rr) ** 2 * (d + 4 * rr)) / 12
     assert 0.0 < 8 * vchain / r["volumes"][-1] < 0.74
+
+
+# ---- the numpy restatement of nematic.py on configurations with known answers -------------------
+def test_order_parameter_known_answers():
+    from oracle import order_params as op
+    cell = np.array([[6.0, 0.0, 0.0], [1.0, 5.0, 0.0], [0.5, -0.7, 7.0]])
+    nb, nc = 4, 6
+    rng = np.random.default_rng(3)
+    # all chains along one direction: P2 = 1
+    u = np.array([0.0, 0.6, 0.8])
+    pos = np.concatenate([rng.uniform(0, 5, 3) + 0.4 * np.arange(nb)[:, None] * u for _ in range(nc)])
+    assert abs(op.nematic_order_param([cell], [pos], nb, nc)[0] - 1.0) < 1e-12
+    # chains along x, y, z in equal numbers: Q = 0, P2 = 0
+    axes = np.eye(3)
+    pos = np.concatenate([rng.uniform(0, 5, 3) + 0.4 * np.arange(nb)[:, None] * axes[c % 3] for c in range(nc)])
+    assert abs(op.nematic_order_param([cell], [pos], nb, nc)[0]) < 1e-12
+    # an end-to-end vector across the periodic boundary is taken at its minimum image
+    far = pos.copy()
+    far[nb - 1] += cell[0]
+    assert np.allclose(op.nematic_order_param([cell], [far], nb, nc), op.nematic_order_param([cell], [pos], nb, nc))
+    # single spheres on lattice points with integer fractional sums: translational order 1; random: ~ 1/sqrt(N)
+    frac = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)]) / 1.0
+    assert abs(op.trans_order_param([cell], [frac @ cell], 1, 27)[0] - 1.0) < 1e-9
+    frac = rng.uniform(0, 1, (4000, 3))
+    assert op.trans_order_param([cell], [frac @ cell], 1, 4000)[0] < 0.06
+    assert op.nematic_order_param([cell], [frac[:27] @ cell], 1, 27)[0] == 0.0
