@@ -387,6 +387,18 @@ def run_b200(args):
         pairs_per_launch = apm * nw * WALKLENGTH * mps
         achieved = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
         achieved_exec = FLOP_PER_PAIR * executed_pairs / (kernel_ms * 1e-3) / 1e12  # (this rank's counter)
+        # HBM side of the same launch: proposals (64 B per move, written by gen_kernel, read by the walk kernel)
+        # + one read and one write of the walker state; shows how far from the HBM roofline the path is
+        hbm_bytes = 2 * 64.0 * nw * WALKLENGTH * mps + 2.0 * nw * (72 + 24 * N + 16)
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except (OSError, ValueError):
+            pass
+        hbm_peak = hbm_peak or 6650.0  # GB/s; fallback of B200_PROFILING.md when the driver's file is absent
+        # dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel, one `ncu --set full` capture of this
+        # workload (profiles/r01_ncu_c2_lean.txt: 188.4 MB + 9.8 MB); other workloads were not captured
+        traffic = 198.2e6 if (name == "C2" and nw == 1024) else None
         line = {
             "metric": "mc_move_attempts_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -403,7 +415,11 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / ffma_peak, "traffic": None,
+                         "frac": achieved / ffma_peak, "traffic": traffic,
+                         "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "note": "state lives in shared memory for the whole walk; the path is latency / "
+                                         "instruction-fetch bound, not HBM bound (DESIGN.md section 3)"},
                          "kernel": walk_kernel_name, "kernel_ms_per_launch": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (ms / args.steps),
                          "algorithmic_pair_tests_per_launch": pairs_per_launch, "flop_per_pair_test": FLOP_PER_PAIR,
