@@ -358,9 +358,10 @@ static bool lean_applies(const hans_cfg *c)
     const int nb = c->nbeads, N = c->nchains * c->nbeads;
     if (!(nb == 1 || nb == 2 || nb == 4 || nb == 6 || nb == 8 || nb == 12)) return false;
     if (N <= 128) return true;
-    // measured (profiles/r01_*): 32 chains x 12 beads 150 vs 112 M moves/s (one CTA of 128 threads per walker);
-    // 128 chains x 6 beads 99 vs 137 -- beyond two waves of chain spheres per move the CTA wins
-    if (nb == 1 || c->nchains > 64) return false;
+    // measured (profiles/r01_*), M moves/s: 32 chains x 12 beads (N = 384) 151 here vs 169 with one CTA of 64
+    // threads per walker vs 110 with 128; 128 chains x 6 beads (N = 768) 99 here vs 137 with 128 threads:
+    // the warp-per-walker kernel keeps the walkers below 256 beads
+    if (nb == 1 || c->nchains > 64 || N >= 256) return false;
     return walker_smem_bytes(N, nb, 32) + cta_extra_bytes(nb, c->nexclude) <= 200 * 1024;
 }
 
@@ -441,7 +442,7 @@ int hans_default_threads_per_walker(const hans_cfg *cfg)
     if (!cfg) return 32;
     const int N = cfg->nchains * cfg->nbeads;
     if (N <= 128) return 32;
-    if (N <= 256) return 64;
+    if (N <= 512) return 64;
     return 128; // (256 threads per walker measured slower at every BASELINE shape: barriers dominate)
 }
 

@@ -75,7 +75,9 @@ def test_host_side_entry_points_and_validation():
     # of up to 64 chains, the cooperative one otherwise
     assert L.hans_default_window(C.byref(cfg)) == 1
     assert L.hans_default_window(C.byref(_lib.make_cfg(64, 1, [1, 192, 0, 0, 3, 3]))) == 1
-    assert L.hans_default_window(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 1
+    assert L.hans_default_window(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 0   # 384 beads: CTA of 64
+    assert L.hans_default_threads_per_walker(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 64
+    assert L.hans_default_window(C.byref(_lib.make_cfg(16, 12, [3, 32, 32, 16, 3, 3]))) == 1
     assert L.hans_default_window(C.byref(big)) == 0                                        # 128 chains: one CTA per walker
     assert L.hans_default_window(C.byref(_lib.make_cfg(16, 5, [1, 1, 1, 1, 1, 1]))) == 0   # nbeads = 5 is not instantiated
     assert L.hans_default_window(C.byref(_lib.make_cfg(200, 1, [1, 1, 0, 0, 1, 1]))) == 0  # 200 spheres
