@@ -426,7 +426,7 @@ __device__ __forceinline__ bool spheres_near(const Filt &f, const float4 a, cons
 // Compaction of the items a wave of T threads flags `near` into LST; returns their number.
 // Collective over the group; the group must synchronise (gsync / gany) before the next call.
 template <int T>
-__device__ __forceinline__ int near_list(const WCtx &w, bool near, int item)
+__device__ __forceinline__ int near_list(const WCtx &w, bool near, int item, bool counter_is_zero = false)
 {
     int *lst = reinterpret_cast<int *>(smem) + w.lst;
     if (T == 32) {
@@ -436,11 +436,23 @@ __device__ __forceinline__ int near_list(const WCtx &w, bool near, int item)
         return __popc(mask);
     } else {
         int *cnt = lst - 4;
-        if (w.lane == 0) *cnt = 0;
-        __syncthreads();
+        if (!counter_is_zero) { // (else the caller zeroed it before its last barrier: one barrier less)
+            if (w.lane == 0) *cnt = 0;
+            __syncthreads();
+        }
         if (near) lst[atomicAdd(cnt, 1)] = item;
         __syncthreads();
         return *cnt;
+    }
+}
+
+// One CTA per walker (T > 32): near-list counter and vote word are zeroed by the caller before the barrier
+// that publishes the trial chain, so a chain move costs four barriers (trial, near list, vote, commit)
+template <int T> __device__ __forceinline__ void coop_reset(const WCtx &w)
+{
+    if (T > 32 && w.lane == 0) {
+        int *z = reinterpret_cast<int *>(smem) + w.lst - 4;
+        z[0] = 0; z[1] = 0;
     }
 }
 
@@ -463,7 +475,7 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
         const int c = cb + w.lane;
         bool near = false;
         if (c < nc && c != ichain) near = spheres_near(f, SM4[f4 + c * nb + m], ct, Rt + SMF[w.rad + c] + 1.001f);
-        const int items = near_list<T>(w, near, c) * nb;
+        const int items = near_list<T>(w, near, c, cb == 0) * nb;
         for (int e = w.lane; e < items; e += T) {
             const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
             const float4 s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
@@ -508,10 +520,16 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
         if (code) return __any_sync(FULL, recheck_chain_exact<T>(w, ichain, b0, (code & 1u) != 0u, (code & 2u) != 0u));
         return false;
     }
-    if (gany<T>(ov)) return true;
-    const bool any_inter = gany<T>(amb), any_intra = intra && gany<T>(amb_intra);
-    if (any_inter || any_intra) return gany<T>(recheck_chain_exact<T>(w, ichain, b0, any_inter, any_intra));
-    return false;
+    {   // T > 32: one barrier for the three flags (warp REDUX, one atomicOr per warp into the zeroed vote word)
+        int *vote = reinterpret_cast<int *>(smem) + w.lst - 3;
+        const unsigned wcode = __reduce_or_sync(FULL, (ov ? 4u : 0u) | (amb ? 1u : 0u) | (amb_intra ? 2u : 0u));
+        if ((threadIdx.x & 31) == 0 && wcode) atomicOr(vote, (int)wcode);
+        __syncthreads();
+        const unsigned code = (unsigned)*vote;
+        if (code & 4u) return true;
+        if (code) return gany<T>(recheck_chain_exact<T>(w, ichain, b0, (code & 1u) != 0u, (code & 2u) != 0u));
+        return false;
+    }
 }
 
 // translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
@@ -524,6 +542,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
     int b0 = 0;
     bool intra = false;
     if (!make_trial(w, p, w.lane, T, cn, c4, b0, intra)) return mkdec(0, HANS_REJ_INVALID, 0.0);
+    coop_reset<T>(w);
     gsync<T>();
     bool ov;
     float Rt = 0.0f;
