@@ -11,6 +11,10 @@ SHAPES = {
     "dimer": (32, 2, [1, 96, 64, 0, 3, 3]),  # the committed input.txt shape
     "C4": (32, 12, [3, 32, 32, 16, 3, 3]),   # BASELINE configs[3], full walker size (384 beads)
     "C5": (128, 6, [1, 384, 256, 384, 3, 3]),  # BASELINE configs[4], full walker size (768 beads)
+    "d40": (40, 2, [2, 40, 30, 0, 3, 3]),      # more than 32 chains of more than one bead: two waves of chain spheres
+    "t3": (11, 3, [2, 20, 20, 0, 3, 3]),       # nbeads the warp-per-walker kernel is not instantiated for, odd nchains
+    "h15": (15, 6, [3, 48, 32, 10, 3, 3]),     # odd number of chains (round robin over chain pairs), dihedrals on
+    "p7": (9, 7, [2, 20, 20, 10, 3, 3]),       # nbeads = 7: cooperative kernel, runtime nbeads, intra-chain pairs
     "tiny": (6, 2, [1, 18, 12, 0, 3, 3]),    # fewer beads than lanes: several lanes share a bead row in box moves
     "tiny1": (5, 1, [1, 15, 0, 0, 3, 3]),
 }

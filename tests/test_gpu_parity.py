@@ -149,7 +149,7 @@ def test_replay_dense_rejections(eng, oracle, tpw):
     assert (dec["reason"] == 1).mean() > 0.2
 
 
-@pytest.mark.parametrize("shape,tpw,density", [("C1", 0, 0.15), ("C1", 64, 0.15), ("C1", 0, 0.45), ("C1", 32, 0.45), ("C1", 128, 0.3), ("C1", 8, 0.45),
+@pytest.mark.parametrize("shape,tpw,density", [("d40", 0, 0.3), ("t3", 0, 0.3), ("h15", 0, 0.2), ("p7", 64, 0.3), ("C1", 0, 0.15), ("C1", 64, 0.15), ("C1", 0, 0.45), ("C1", 32, 0.45), ("C1", 128, 0.3), ("C1", 8, 0.45),
                                                 ("C4s", 0, 0.4), ("C4s", 64, 0.4), ("dimer", 0, 0.5), ("tiny", 0, 0.5)])
 def test_replay_dense_chains(eng, oracle, shape, tpw, density):
     """Chain systems compressed until the chains' bounding spheres touch many neighbours and the cell is only a
@@ -205,7 +205,9 @@ def test_replay_invalid_and_edge(eng, oracle):
                                                ("C1", 0, 6), ("C1", 1, 6), ("C1", 8, 4), ("C2", 0, 10), ("C2", 8, 6),
                                                ("C2", 1, 6), ("C4s", 0, 3), ("C4s", 8, 3), ("dimer", 0, 5), ("dimer", 8, 5),
                                                ("tiny", 0, 12), ("tiny", 32, 12), ("tiny1", 0, 12), ("tiny1", 64, 12),
-                                               ("C4", 0, 1), ("C4", 128, 1), ("C5", 0, 1), ("C5", 128, 1), ("C5", 256, 1)])
+                                               ("C4", 0, 1), ("C4", 128, 1), ("C5", 0, 1), ("C5", 128, 1), ("C5", 256, 1),
+                                               ("d40", 0, 6), ("d40", 32, 6), ("d40", 64, 6), ("t3", 0, 8), ("t3", 64, 8),
+                                               ("h15", 0, 6), ("h15", 8, 6), ("h15", 128, 6), ("p7", 0, 6), ("p7", 64, 6)])
 def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     nw = 10 if shape not in ("C4", "C5") else 7
     cfg, H, R, k = make_walkers(shape, nw, seed=31)
