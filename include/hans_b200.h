@@ -99,7 +99,8 @@ int hans_device_count(void);
 int64_t hans_walker_smem_bytes(const hans_cfg *cfg);
 /* MCNS.py:296-301 */
 int hans_moves_per_sweep(int nbeads, int nchains);
-/* default threads per walker for a shape (32 = one warp per walker, else one CTA per walker) */
+/* threads per walker of the cooperative kernel for a shape (32 = one warp per walker, four walkers
+ * per CTA; 64 / 128 = one CTA per walker) */
 int hans_default_threads_per_walker(const hans_cfg *cfg);
 /* window size the warp-per-walker kernel uses for a shape when threads_per_walker = 0 (1 = one
  * move at a time, 8 = speculative windows); 0 = the shape runs on the cooperative kernel */
@@ -115,12 +116,14 @@ int hans_default_window(const hans_cfg *cfg);
  * d_pair_tests        device scalar, executed pair tests accumulated (may be NULL)
  * threads_per_walker  32, 64, 128, 256: cooperative kernel, the walker's threads share every move
  *                     (32 = one warp per walker, else one CTA per walker);
- *                     1, 8: warp-per-walker kernel specialised on nbeads (needs nchains*nbeads
- *                     <= 128, nbeads in {1,2,4,6,8,12}); 1 = one move at a time, 8 = speculative
- *                     windows of up to 8 consecutive single-chain moves, settled in order (same
+ *                     1, 8: warp-per-walker kernel specialised on nbeads (nbeads in
+ *                     {1,2,4,6,8,12}; up to 128 beads, or chains of up to 64 chains and fewer than
+ *                     256 beads); 1 = one move at a time, 8 = speculative windows of up to 8
+ *                     consecutive single-chain moves, settled in order (<= 128 beads; same
  *                     decisions and trajectory, bit for bit);
- *                     0 = hans_default_window if the shape qualifies, else
- *                     hans_default_threads_per_walker
+ *                     0 = the measured default per shape: hans_default_window if non-zero, else
+ *                     hans_default_threads_per_walker.
+ *                     Every variant produces the same trajectory; the choice is speed only.
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
                       const int32_t *d_ids, int n_active, int sweeps,
