@@ -25,6 +25,39 @@
 
 namespace hb {
 
+// Shared-memory accesses of the hottest path (single-sphere translation) through ONE 32-bit shared base kept in a
+// register.  nvcc forms every address of the `extern __shared__` symbol with S2R SR_CgaCtaId + LEA; at the head of
+// a move that chain is pure latency in front of the first load (profiles/r01_ncu_c2_lean.txt, SASS view).
+__device__ __forceinline__ unsigned shared_base()
+{
+    unsigned b = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("" : "+r"(b)); // opaque: keep it in a register instead of recomputing it
+    return b;
+}
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(unsigned a)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_f4(unsigned a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // cell inverse + filter parameters of the current cell, in registers
 struct CellRegs {
     double Hi[9];
@@ -58,17 +91,20 @@ __device__ __noinline__ DecP lean_move_chain_generic(WCtx w, int q)
 
 // single spheres (NB == 1), translation: alk.alkane_translate_chain + accept/restore
 // (MCNS.py:323,371-380).  Returns 1 accepted / 0 overlap.
-__device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRegs &cr, const PropRec *p, int ichain,
+__device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRegs &cr, unsigned sb, int q, int ichain,
                                                      unsigned &pairs)
 {
-    const int P = W_P(w) + 3 * ichain, f4 = W_F4(w), N = w.N;
-    const double x = smem[P] + p->p[0], y = smem[P + 1] + p->p[1], z = smem[P + 2] + p->p[2];
+    const int N = w.N;
+    const unsigned pa = sb + 64u * (unsigned)(w.ring + q);             // the proposal record
+    const unsigned Pa = sb + 8u * (unsigned)(W_P(w) + 3 * ichain);     // the bead (float64)
+    const unsigned fa = sb + 16u * (unsigned)W_F4(w);                  // the shadows
+    const double x = lds_f64(Pa) + lds_f64(pa + 16), y = lds_f64(Pa + 8) + lds_f64(pa + 24), z = lds_f64(Pa + 16) + lds_f64(pa + 32);
     const float4 cs = shadow_of(x, y, z, cr.Hi);
     const Filt &f = cr.f;
     float rmin = 3.0e38f; // smallest float32 r^2 over the beads this lane owns
 #pragma unroll 2
     for (int j = w.lane; j < N; j += 32) {
-        const float4 s = SM4[f4 + j];
+        const float4 s = lds_f4(fa + 16u * (unsigned)j);
         const float r2 = r2_f32(f, s.x - cs.x, s.y - cs.y, s.z - cs.z);
         rmin = (j != ichain) ? fminf(rmin, r2) : rmin;
     }
@@ -85,10 +121,10 @@ __device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRe
         __syncwarp();
         overlap = lean_recheck(w, ichain, 0, true, false);
     }
-    if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
+    if (!overlap && (lds_f64(pa + 48) < 1.0)) { // MCNS.py:372 with boltz = 1 (u_acc)
         if (w.lane == 0) {
-            smem[P] = x; smem[P + 1] = y; smem[P + 2] = z;
-            SM4[f4 + ichain] = cs;
+            sts_f64(Pa, x); sts_f64(Pa + 8, y); sts_f64(Pa + 16, z);
+            sts_f4(fa + 16u * (unsigned)ichain, cs);
         }
         __syncwarp();
     }
@@ -287,6 +323,7 @@ __global__ void __launch_bounds__(32, HANS_LEAN_MIN_CTAS) walk_lean_kernel(const
         const int wi = a.ids ? a.ids[k] : k;
         load_walker<T>(w, a.H, a.R, wi, true);
         CellRegs cr = load_cell_regs(w);
+        const unsigned sb = shared_base();
         const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
         unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
         unsigned pairs = 0;
@@ -336,13 +373,19 @@ __global__ void __launch_bounds__(32, HANS_LEAN_MIN_CTAS) walk_lean_kernel(const
                     }
                 }
                 const PropRec *p = ring + q;
-                const int4 hd = *reinterpret_cast<const int4 *>(p); // type, ichain, idx0, idx1
-                const int type = hd.x, ichain = hd.y;
+                int type, ichain, idx0;
+                if (NB == 1) {
+                    const int2 h2 = lds_i2(sb + 64u * (unsigned)(w.ring + q)); // type, ichain
+                    type = h2.x; ichain = h2.y; idx0 = 0;
+                } else {
+                    const int4 hd = *reinterpret_cast<const int4 *>(p); // type, ichain, idx0, idx1
+                    type = hd.x; ichain = hd.y; idx0 = hd.z;
+                }
                 const bool chain_ok = (unsigned)ichain < (unsigned)w.nc;
                 if (NB == 1 && type == HANS_TRANS && chain_ok) {
-                    accmask |= (unsigned)lean_translate_sphere(w, cr, p, ichain, pairs) << q;
+                    accmask |= (unsigned)lean_translate_sphere(w, cr, sb, q, ichain, pairs) << q;
                 } else if (NB > 1 && chain_ok &&
-                           (type == HANS_TRANS || type == HANS_ROT || (type == HANS_DIH && NB >= 4 && hd.z >= 3 && hd.z <= NB - 1))) {
+                           (type == HANS_TRANS || type == HANS_ROT || (type == HANS_DIH && NB >= 4 && idx0 >= 3 && idx0 <= NB - 1))) {
                     accmask |= (unsigned)lean_move_chain<(NB > 1 ? NB : 2)>(w, cr, p, ichain, pairs) << q;
                 } else {
                     DecP d;
