@@ -188,18 +188,23 @@ def test_hard_sphere_equation_of_state_gpu(eng):
                                                    (32, 12, [3, 32, 32, 16, 3, 3], 512)])      # C4, one GPU's share at 8 GPUs
 def test_full_size_invariants(eng, nchains, nbeads, mr, nw):
     sweeps = 40 if nbeads < 12 else 8
-    pa = _pool(eng, nw, nchains, nbeads, mr, seed=2026, threads_per_walker=32)
-    pb = _pool(eng, nw, nchains, nbeads, mr, seed=2026, threads_per_walker=128)
+    pa = _pool(eng, nw, nchains, nbeads, mr, seed=2026, threads_per_walker=0)     # the default kernel of the shape
+    pb = _pool(eng, nw, nchains, nbeads, mr, seed=2026, threads_per_walker=128)   # one CTA of 128 threads per walker
+    pc = _pool(eng, nw, nchains, nbeads, mr, seed=2026, threads_per_walker=32)    # cooperative, one warp per walker
     Ha, Ra = pa.get_state()
     Hb, Rb = pb.get_state()
     assert np.array_equal(Ra, Rb)
     limit = float(pa.vol.max().item())
     att, acc = pa.mc_run(sweeps, volume_limit=limit)
     pb.mc_run(sweeps, volume_limit=limit)
+    pc.workspace_bytes = 0                                                          # proposals generated inside the kernel
+    pc.mc_run(sweeps, volume_limit=limit)
     Ha, Ra = pa.get_state()
     Hb, Rb = pb.get_state()
-    # the trajectory does not depend on how many threads cooperate on a walker
+    Hc, Rc = pc.get_state()
+    # the trajectory does not depend on the kernel variant, the threads per walker or where proposals are generated
     assert np.array_equal(Ha, Hb) and np.array_equal(Ra, Rb)
+    assert np.array_equal(Ha, Hc) and np.array_equal(Ra, Rc)
     assert not pa.check_overlap().cpu().numpy().any()                               # hard-sphere constraint
     vol, mar, mcos = (t.cpu().numpy() for t in pa.cell_metrics())
     assert (vol <= limit * (1 + 1e-12)).all()                                       # volume ceiling, MCNS.py:351
