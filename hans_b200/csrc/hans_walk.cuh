@@ -328,7 +328,7 @@ __device__ __forceinline__ bool chain_overlaps(const WCtx &w, int ichain, int b0
 // Trial chain of a translate / rotate / dihedral proposal, built from the CURRENT chain: beads
 // first, first+stride, ... are written to smem[cn + 3b ..] (float64) and SM4[c4 + b] (shadows).
 // Returns false for a malformed dihedral proposal.  One copy of this arithmetic serves both the
-// cooperative path (first = lane, stride = T) and the speculative windows (hans_spec.cuh).
+// cooperative path (first = lane, stride = T) and the speculative windows (hans_lean.cuh).
 __device__ __forceinline__ bool make_trial(const WCtx &w, const PropRec *p, int first, int stride, int cn, int c4,
                                            int &b0, bool &intra)
 {
