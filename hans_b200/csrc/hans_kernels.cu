@@ -6,6 +6,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo  (see
 // __graft_entry__.build()).  -fmad=false is REQUIRED for bit-exact parity with the CPU checker.
 #include "hans_lean.cuh"
+#include "hans_team.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -343,7 +344,7 @@ static int grid_for(int n, int T)
 
 static int pick_T(const hans_cfg *c, int T)
 {
-    if (T == 0 || (T >= 1 && T <= 8)) T = hans_default_threads_per_walker(c); // 1..8 only steer the walk kernels
+    if (T >= 0 && T < 32) T = hans_default_threads_per_walker(c); // 1..31 only steer the walk kernels
     if (T != 32 && T != 64 && T != 128 && T != 256) return -1;
     return T;
 }
@@ -404,6 +405,44 @@ static int pick_W(const hans_cfg *c, int tpw)
     return (tpw == 1 || tpw == 8) ? tpw : -1;
 }
 
+// One CTA of NWARP warps per walker, one warp per move of a speculative window (hans_team.cuh): chains only
+// (the pruning works on chain bounding spheres), and the walker plus NWARP trial chains must fit shared memory.
+static size_t team_smem_bytes(const hans_cfg *c, int nwarp)
+{
+    return walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp) +
+           team_tail_bytes(nwarp) + cta_extra_bytes(c->nbeads, c->nexclude);
+}
+static bool team_applies(const hans_cfg *c, int nwarp)
+{
+    return c->nbeads > 1 && c->nchains >= 2 && team_smem_bytes(c, nwarp) <= 227 * 1024;
+}
+
+template <bool REPLAY> static int launch_team(const WalkArgs &a, int nwarp, cudaStream_t st)
+{
+    const hans_cfg *c = &a.cfg;
+    const size_t smem = team_smem_bytes(c, nwarp);
+    const int cap = sm_count() * 8, grid = a.n_active < cap ? a.n_active : cap;
+    int rc = HANS_OK;
+#define TEAM_LAUNCH(NN, WW)                                                        \
+    {                                                                              \
+        rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY>, smem);                  \
+        if (rc) return rc;                                                         \
+        walk_team_kernel<NN, WW, REPLAY><<<grid, 32 * WW, smem, st>>>(a);          \
+    }
+#define TEAM_NB(WW)                                                                \
+    switch (c->nbeads) {                                                           \
+    case 6: TEAM_LAUNCH(6, WW); break;                                             \
+    case 12: TEAM_LAUNCH(12, WW); break;                                           \
+    default: TEAM_LAUNCH(0, WW); break;                                            \
+    }
+    if (nwarp == 4) { TEAM_NB(4); }
+    else { TEAM_NB(8); }
+#undef TEAM_NB
+#undef TEAM_LAUNCH
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
 #define DISPATCH_T(T, ...)                                    \
     switch (T) {                                              \
     case 32: { constexpr int TT = 32; __VA_ARGS__; } break;   \
@@ -459,14 +498,20 @@ int hans_default_window(const hans_cfg *cfg)
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
 {
     int rc = HANS_OK;
-    if (threads_per_walker < 32 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
+    if ((threads_per_walker == 24 || threads_per_walker == 28) && a.mode == HANS_MODE_FUSED) {
+        const int nwarp = threads_per_walker - 20;
+        if (!team_applies(cfg, nwarp))
+            return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
+        return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
+    }
+    if (threads_per_walker < 24 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
         const int W = pick_W(cfg, threads_per_walker);
         if (W > 0) return from_memory ? launch_lean<true>(a, W, st) : launch_lean<false>(a, W, st);
         if (threads_per_walker != 0)
             return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
     }
     const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 32, 64, 128 or 256");
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 24, 28, 32, 64, 128 or 256");
     const size_t smem = cta_smem_bytes(cfg, T);
     if (from_memory) {
         DISPATCH_T(T, {

@@ -117,9 +117,10 @@ __host__ __device__ inline size_t window_smem_bytes(int nb, int W)
     return (((size_t)W * nb * 40) + 63) & ~(size_t)63;
 }
 
-// GPC walker groups of T threads per CTA; W > 0 adds the window area behind each walker's ring
+// GPC walker groups of T threads per CTA; W > 0 adds the window area behind each walker's ring, `tail` bytes
+// (a multiple of 64) behind that
 template <int T, int GPC>
-__device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W)
+__device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail = 0)
 {
     WCtx w;
     w.nb = c.nbeads; w.nc = c.nchains; w.N = c.nbeads * c.nchains; w.nex = c.nexclude;
@@ -127,7 +128,7 @@ __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W)
     w.lane = threadIdx.x % T;
     const int g = threadIdx.x / T;
     const int core = (int)walker_smem_bytes(w.N, w.nb, T);
-    const int per = core + (int)window_smem_bytes(w.nb, W);
+    const int per = core + (int)window_smem_bytes(w.nb, W) + tail;
     const int base = per * g;                                           // bytes
     w.D0 = base / 8;
     const int dbytes = ((8 * (6 * w.N + 3 * w.nb + 36)) + 15) & ~15;
@@ -621,8 +622,11 @@ __device__ __noinline__ bool trial_overlap_exact(WCtx w, bool with_intra)
 
 // Box moves of chain systems: all pairs of CHAINS through their bounding spheres (round robin over
 // the chains: item p = (row ci, offset d), cj = ci + d mod nc), bead level only for the pairs of
-// chains that survive, one wave of T chain pairs at a time.  Pairs of beads inside the filter's band
-// are settled in float64 at the end (first one per thread; more than one -> the full float64 pass).
+// chains that survive.  Every WARP works through its own waves of 32 chain pairs (ballot compaction into
+// its 32 entries of LST, bead tests of the survivors) without a CTA-wide barrier; a warp that finds a
+// certain overlap raises a flag the others poll, so a rejected move still ends early.  One vote at the
+// end.  Pairs of beads inside the filter's band are settled in float64 at the end (first one per thread;
+// more than one -> the full float64 pass).  The caller zeroes the flag before its last barrier (T > 32).
 template <int T>
 __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_intra, unsigned &pairs)
 {
@@ -630,12 +634,14 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
     const int nb = w.nb, nc = w.nc, m = nb >> 1, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18;
     const int half = nc >> 1, nitems = nc * half;
     const bool even = (nc & 1) == 0;
-    const int *lst = reinterpret_cast<const int *>(smem) + w.lst;
+    const int ln = w.lane & 31, w0 = w.lane & ~31;
+    int *lst = reinterpret_cast<int *>(smem) + w.lst + w0;
+    volatile int *flag = reinterpret_cast<volatile int *>(smem) + w.lst - 3;
     bool ov = false;
     int namb = 0, ai = 0, aj = 0;
 #pragma unroll 1
-    for (int p0 = 0; p0 < nitems; p0 += T) {
-        const int p = p0 + w.lane;
+    for (int p0 = w0; p0 < nitems; p0 += T) {
+        const int p = p0 + ln;
         bool near = false;
         int packed = 0;
         if (p < nitems) {
@@ -649,9 +655,12 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
                 pairs += 1;
             }
         }
-        const int items = near_list<T>(w, near, packed) * nb;
+        const unsigned mask = __ballot_sync(FULL, near);
+        if (near) lst[__popc(mask & ((1u << ln) - 1u))] = packed;
+        __syncwarp();
+        const int items = __popc(mask) * nb;
 #pragma unroll 1
-        for (int e = w.lane; e < items; e += T) {
+        for (int e = ln; e < items; e += 32) {
             const int pi = div_nb(w, e);
             const int pk = lst[pi];
             const int bi = (pk >> 16) * nb + (e - pi * nb), cj0 = (pk & 0xffff) * nb;
@@ -668,7 +677,13 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
             }
             pairs += (unsigned)nb;
         }
-        if (gany<T>(ov)) return true; // (also the barrier before LST is rewritten)
+        // (the vote also orders this wave's reads of LST before the next wave's writes)
+        if (T == 32) {
+            if (__any_sync(FULL, ov)) return true;
+        } else {
+            if (__any_sync(FULL, ov)) *flag = 1;
+            if (__any_sync(FULL, *flag != 0)) break;
+        }
     }
     if (with_intra && w.npc > 0) { // same-chain pairs further apart than nexclude (shear / stretch, MCNS.py:198,247)
         const uchar2 *tab = W_ITAB(w);
@@ -687,8 +702,8 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
             }
             pairs += 1;
         }
-        if (gany<T>(ov)) return true;
     }
+    if (gany<T>(ov)) return true;
     if (gany<T>(namb > 0)) {
         if (namb > 0)
             ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj] - smem[tp + 3 * ai], smem[tp + 3 * aj + 1] - smem[tp + 3 * ai + 1],
@@ -876,6 +891,7 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
     gsync<T>();
     follow_cell<T>(w, W_P(w), W_TP(w), W_G4(w), sh + 9, sh + 18, sh + 27); // alk.alkane_change_box, MCNS.py:186,238
     filter_params(sh + 18, W_SF(w) + SF_TRIAL, w.lane == 0);
+    if (T > 32 && w.lane == 0) reinterpret_cast<int *>(smem)[w.lst - 3] = 0; // the early-exit flag of trial_overlap_pruned
     gsync<T>();
     int reason = HANS_ACCEPT;
     if (!is_vol) {

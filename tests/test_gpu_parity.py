@@ -122,12 +122,13 @@ def _replay_case(eng, oracle, shape, tpw, nwalkers=12, nmoves=400, seed=21, dens
 
 
 # tpw 32..256: cooperative kernel; tpw 1 / 8: warp-per-walker kernel, one move at a time / speculative
-# windows of 8 moves; 0: default
+# windows of 8 moves; 24 / 28: one CTA of 4 / 8 warps per walker, one warp per move of a window; 0: default
 @pytest.mark.parametrize("shape,tpw", [("C1", 32), ("C1", 128), ("C2", 32), ("C2", 64), ("C4s", 32), ("C4s", 256),
                                         ("dimer", 32), ("C1", 0), ("C1", 1), ("C1", 8), ("C2", 0), ("C2", 1), ("C2", 8),
                                         ("C4s", 0), ("C4s", 1), ("C4s", 8), ("dimer", 0), ("dimer", 1), ("dimer", 8),
                                         ("tiny", 0), ("tiny", 8), ("tiny", 32), ("tiny", 64), ("tiny1", 0), ("tiny1", 32),
-                                        ("tiny1", 128)])
+                                        ("tiny1", 128), ("C1", 24), ("C1", 28), ("C4s", 24), ("C4s", 28), ("dimer", 24),
+                                        ("tiny", 28), ("p7", 24), ("t3", 28)])
 def test_replay_all_moves(eng, oracle, shape, tpw):
     # equal weights so that every move type (incl. dihedral where nbeads >= 4) is exercised
     nchains, nbeads, _ = SHAPES[shape]
@@ -150,7 +151,9 @@ def test_replay_dense_rejections(eng, oracle, tpw):
 
 
 @pytest.mark.parametrize("shape,tpw,density", [("d40", 0, 0.3), ("t3", 0, 0.3), ("h15", 0, 0.2), ("p7", 64, 0.3), ("C1", 0, 0.15), ("C1", 64, 0.15), ("C1", 0, 0.45), ("C1", 32, 0.45), ("C1", 128, 0.3), ("C1", 8, 0.45),
-                                                ("C4s", 0, 0.4), ("C4s", 64, 0.4), ("dimer", 0, 0.5), ("tiny", 0, 0.5)])
+                                                ("C4s", 0, 0.4), ("C4s", 64, 0.4), ("dimer", 0, 0.5), ("tiny", 0, 0.5),
+                                                ("C1", 24, 0.45), ("C1", 28, 0.3), ("C4s", 28, 0.4), ("d40", 24, 0.3),
+                                                ("h15", 28, 0.2), ("p7", 24, 0.3), ("tiny", 28, 0.5)])
 def test_replay_dense_chains(eng, oracle, shape, tpw, density):
     """Chain systems compressed until the chains' bounding spheres touch many neighbours and the cell is only a
     few diameters wide: the chain-level pruning keeps most neighbours (or, once the bounding distance exceeds half
@@ -165,7 +168,8 @@ def test_replay_dense_chains(eng, oracle, shape, tpw, density):
     assert (dec["reason"] == 1).mean() > 0.02 and dec["accepted"].mean() > 0.05
 
 
-@pytest.mark.parametrize("shape,tpw", [("C2", 8), ("C1", 8), ("C4s", 8), ("dimer", 8)])
+@pytest.mark.parametrize("shape,tpw", [("C2", 8), ("C1", 8), ("C4s", 8), ("dimer", 8), ("C1", 24), ("C1", 28), ("C4s", 28),
+                                        ("dimer", 24), ("d40", 28), ("h15", 24)])
 def test_replay_windows_only_chain_moves(eng, oracle, shape, tpw):
     """No box moves at all: every window of the speculative path is full, and with small steps most
     moves are accepted, so the in-window fix-ups and stale re-evaluations carry the result."""
@@ -176,6 +180,48 @@ def test_replay_windows_only_chain_moves(eng, oracle, shape, tpw):
     finally:
         del SHAPES["_tmp"]
     assert dec["accepted"].mean() > 0.5
+
+
+@pytest.mark.parametrize("tpw", [0, 1, 8, 24, 28, 64])
+def test_replay_band_hits(eng, oracle, tpw):
+    """Contacts at 1 +- 1e-9 .. 1e-13: the float32 filter cannot decide (its band is ~1e-5 wide), float64 must,
+    in every kernel -- in the windowed kernels also when the partner is a chain an EARLIER move of the same window
+    has just put there (proposals a_i, b_i below)."""
+    from hans_b200 import _lib
+    nw, L = 4, 20.0
+    nchains, nbeads, mr = SHAPES["dimer"]
+    k = dict(dv_max=2.0, dr_max=2.0, dt_max=0.43, dh_max=0.4, dshear=1.0, dstretch=1.0)
+    cfg = oracle.make_cfg(nchains, nbeads, mr, **k)
+    H = np.tile(np.diag([L, L, L]), (nw, 1, 1)).astype(np.float64)
+    sites = np.array([(1.5 + 3.0 * i, 1.5 + 3.0 * j, 3.0) for i in range(6) for j in range(6)])[:nchains]
+    R = np.zeros((nw, nchains * nbeads, 3))
+    R[:, 0::2] = sites
+    R[:, 1::2] = sites + np.array([0.4, 0.0, 0.0])
+    deltas = [1e-9, -1e-9, 1e-12, -1e-12, 1e-13, -1e-13, 3e-7, -3e-7, 0.0, 2e-16]
+    props = np.zeros((nw, 22), dtype=oracle.PROPOSAL_DTYPE)
+    props["type"] = 1
+    props["u_acc"] = 0.5
+    for w in range(nw):
+        for i in range(10):      # mover 10 + i lands on top of anchor i, at 1 + delta
+            d = deltas[(i + w) % len(deltas)]
+            props["ichain"][w, i] = 10 + i
+            props["p"][w, i, :3] = sites[i] + np.array([0.0, 0.0, 1.0 + d]) - sites[10 + i]
+        for i in range(6):       # a_i = chain 20 + i goes up; b_i = chain 26 + i lands beside its NEW position
+            d = deltas[(3 * i + w) % len(deltas)]
+            props["ichain"][w, 10 + 2 * i] = 20 + i
+            props["p"][w, 10 + 2 * i, :3] = [0.0, 0.0, 5.0]
+            props["ichain"][w, 11 + 2 * i] = 26 + i
+            props["p"][w, 11 + 2 * i, :3] = sites[20 + i] + np.array([0.0, 1.0 + d, 5.0]) - sites[26 + i]
+    H0, R0 = H.copy(), R.copy()
+    want = np.stack([oracle.replay(cfg, H[w], R[w], props[w], 1e300, 0) for w in range(nw)])  # (advances H, R)
+    assert 0.2 < want["accepted"].mean() < 0.95
+    _lib.diag_counters(reset=True)
+    pool = make_pool(eng, "dimer", H0, R0, k, tpw=tpw)
+    got = pool.replay(None, props, volume_limit=1e300, mode=0)
+    for f in ("accepted", "reason"):
+        assert np.array_equal(got[f], want[f]), f
+    assert_state_equal(pool, H, R)
+    assert _lib.diag_counters()[0] >= nw * 10  # the float64 settle really ran
 
 
 def test_replay_propose_mode(eng, oracle):
@@ -207,7 +253,9 @@ def test_replay_invalid_and_edge(eng, oracle):
                                                ("tiny", 0, 12), ("tiny", 32, 12), ("tiny1", 0, 12), ("tiny1", 64, 12),
                                                ("C4", 0, 1), ("C4", 128, 1), ("C5", 0, 1), ("C5", 128, 1), ("C5", 256, 1),
                                                ("d40", 0, 6), ("d40", 32, 6), ("d40", 64, 6), ("t3", 0, 8), ("t3", 64, 8),
-                                               ("h15", 0, 6), ("h15", 8, 6), ("h15", 128, 6), ("p7", 0, 6), ("p7", 64, 6)])
+                                               ("h15", 0, 6), ("h15", 8, 6), ("h15", 128, 6), ("p7", 0, 6), ("p7", 64, 6),
+                                               ("C1", 24, 6), ("C4s", 28, 3), ("C4", 24, 1), ("C4", 28, 1), ("C5", 24, 1),
+                                               ("C5", 28, 1), ("d40", 28, 6), ("h15", 24, 6), ("p7", 28, 6), ("t3", 24, 8)])
 def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     nw = 10 if shape not in ("C4", "C5") else 7
     cfg, H, R, k = make_walkers(shape, nw, seed=31)
@@ -234,7 +282,7 @@ def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
 
 
 @pytest.mark.parametrize("shape,tpw,ws_moves", [("C2", 0, 0), ("C2", 0, 96), ("C1", 0, 64), ("C1", 32, 32), ("C4s", 128, 0),
-                                                 ("C4s", 128, 160), ("dimer", 1, 32)])
+                                                 ("C4s", 128, 160), ("dimer", 1, 32), ("C4s", 24, 160), ("C1", 28, 64)])
 def test_mc_run_proposals_ahead(eng, oracle, shape, tpw, ws_moves):
     """hans_mc_run_batch_ws: proposals generated ahead of the walk into a workspace (default), with a
     workspace so small that the walk is cut into chunks, and without one (generation in the kernel)."""
