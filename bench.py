@@ -286,7 +286,12 @@ def run_b200(args):
     import ctypes as C
     win = _lib.lib.hans_default_window(C.byref(pool.cfg)) if args.tpw == 0 else (args.tpw if args.tpw < 32 else 0)
     tpw_coop = args.tpw if args.tpw >= 32 else _lib.lib.hans_default_threads_per_walker(C.byref(pool.cfg))
+    team = (_lib.lib.hans_default_team(C.byref(pool.cfg)) if args.tpw == 0 and not win
+            else (args.tpw - 20 if args.tpw in (24, 28) else 0))
+    if team:
+        win = 0
     walk_kernel_name = (f"hb::walk_lean_kernel<NB={nbeads},W={win}> (one warp per walker)" if win
+                        else f"hb::walk_team_kernel<NB={nbeads if nbeads in (6, 12) else 0},NWARP={team}> (one CTA per walker, one warp per move)" if team
                         else f"hb::walk_kernel<T={tpw_coop}> (one CTA per walker)") + " + hb::gen_kernel"
     # FP32 FFMA issue peak of this GPU (roofline denominator; MEASURED_PEAKS.json has no FP32 figure)
     ffma_peak = engine.ffma_peak_tflops()

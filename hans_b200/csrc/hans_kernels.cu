@@ -495,9 +495,23 @@ int hans_default_window(const hans_cfg *cfg)
     return 1;
 }
 
+int hans_default_team(const hans_cfg *cfg)
+{
+    if (!cfg || check_cfg(cfg) != HANS_OK) return 0;
+    // Measured on B200 (profiles/r01_probe_team_kernel.jsonl), M moves/s: 128 chains x 6 beads 148 (CTA of 128 threads
+    // sharing every move) vs 265 / 343 with 4 / 8 warps, one move each; 32 chains x 12 beads 169 (CTA of 64) vs 199 / 140
+    // (windows of distinct chains are short with 32 chains); 16 x 6 beads: the warp-per-walker kernel stays 2x ahead.
+    if (cfg->nbeads < 2 || cfg->nchains * cfg->nbeads < 256) return 0;
+    if (cfg->nchains >= 64 && team_applies(cfg, 8)) return 8;
+    if (cfg->nchains >= 24 && team_applies(cfg, 4)) return 4;
+    return 0;
+}
+
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
 {
     int rc = HANS_OK;
+    if (threads_per_walker == 0 && a.mode == HANS_MODE_FUSED && !lean_applies(cfg) && hans_default_team(cfg))
+        threads_per_walker = 20 + hans_default_team(cfg);
     if ((threads_per_walker == 24 || threads_per_walker == 28) && a.mode == HANS_MODE_FUSED) {
         const int nwarp = threads_per_walker - 20;
         if (!team_applies(cfg, nwarp))

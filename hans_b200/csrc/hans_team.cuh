@@ -11,11 +11,12 @@
 // plain chain moves of DISTINCT chains is evaluated at once:
 //   A1  warp k builds the trial chain of move k from the current state (its chain is not touched
 //       by moves 0..k-1 of the window, so this is the state the serial order would have used);
-//   --  barrier
 //   A2  warp k tests its trial chain, with chain-level pruning and the float32 filter, against
 //       every chain that no earlier move of the window touches (these are where the serial order
-//       would have them), and against the chains of the earlier moves j < k twice: at their old
-//       position (bit j of `old`) and at their trial position (bit j of `new`);
+//       would have them);
+//   --  barrier
+//   A3  ... and against the chains of the earlier moves j < k twice: at their old position (bit j
+//       of `old`) and at their trial position (bit j of `new`), bounding spheres first;
 //   --  barrier
 //   B   every thread settles the window in order (a few integer operations): move k overlaps iff
 //       its base test did, or for some j < k: committed[j] ? new[j] : old[j].  A move with a pair
@@ -34,35 +35,44 @@
 
 namespace hb {
 
-// behind the window area: res[8] (result word per move of the window), plain[8] / ucm[8] (masks of the batch: plain
-// single-chain moves, moves with u_acc < 1), rtw[8] (bounding radii of the window's trial chains), then one near
-// list of TEAM_LIST chains per warp
+// behind the window area (int offsets from `res`): res[8] result word per move of the window; rtw[8] (at 24) bounding
+// radii of the window's trial chains; meta[T + 8] (at 32) per move of the batch: chain | (u_acc < 1) << 30 for a plain
+// single-chain move, -1 otherwise; info[T] (at 40 + T) per move: length of the window that starts there | commit mask
+// << 8; then (at 48 + 2 T) one near list of TEAM_LIST chains per warp; then 32 float4 per warp: the shadows of the
+// beads of one pass that lie inside the trial chain's bounding sphere
 #define TEAM_WAVES 4
 #define TEAM_LIST (32 * TEAM_WAVES)
-__host__ __device__ constexpr int team_tail_bytes(int nwarp) { return 128 + 4 * TEAM_LIST * nwarp; }
+#ifndef HANS_TEAM_BEAD_PRUNE
+#define HANS_TEAM_BEAD_PRUNE 1
+#endif
+__host__ __device__ constexpr int team_tail_bytes(int nwarp) { return 192 + 256 * nwarp + 4 * TEAM_LIST * nwarp + 512 * nwarp; }
 
-// A2 for move k of the window `win` (warp-uniform arguments).  Result word, uniform over the warp:
+// A2 for move k of the window (warp-uniform arguments; called by ALL warps, `active` = this warp has a move: there
+// is a CTA barrier inside).  `wmeta` = the window's entries of meta[].  Result word, uniform over the warp:
 // bit 0 certain overlap with a chain no earlier move touches, bit 1 a pair inside the band somewhere,
 // bits 8+j / 16+j certain overlap with the chain of move j at its old / trial position.
 template <int NB, int NWARP>
-__device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, const PropRec *win, int *lst, const float *rtw, int k, int ln,
-                                              int ichain, int b0, bool intra, float Rt, unsigned &pairs)
+__device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, const int *wmeta, int *lst, float4 *buf, const float *rtw,
+                                              bool active, int k, int ln, int ichain, int b0, bool intra, float Rt,
+                                              unsigned &pairs)
 {
     const int nb = NB ? NB : w.nb, nc = w.nc, m = nb >> 1, f4 = W_F4(w), c4 = w.w4 + nb * k;
     int early[NWARP > 1 ? NWARP - 1 : 1];
 #pragma unroll
-    for (int j = 0; j < NWARP - 1; ++j) early[j] = j < k ? win[j].ichain : -1;
+    for (int j = 0; j < NWARP - 1; ++j) early[j] = j < k ? (wmeta[j] & 0xffff) : -1;
+#if !HANS_TEAM_BEAD_PRUNE
     float4 tr[NB ? NB : 1];
     if (NB) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) tr[b] = SM4[c4 + b];
     }
+#endif
     const float4 ct = SM4[c4 + m];
     bool ov = false, amb = false;
     // TEAM_WAVES waves of 32 chain spheres at a time (independent tests in flight), ONE compaction, one pass over
     // the beads of the survivors
 #pragma unroll 1
-    for (int cb = 0; cb < nc; cb += TEAM_LIST) {
+    for (int cb = 0; active && cb < nc; cb += TEAM_LIST) {
         bool near[TEAM_WAVES];
 #pragma unroll
         for (int u = 0; u < TEAM_WAVES; ++u) {
@@ -87,6 +97,38 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
         }
         __syncwarp();
         const int items = cnt * nb;
+#if HANS_TEAM_BEAD_PRUNE
+        // bead level, two steps: which beads of the near chains lie inside the trial chain's bounding sphere (+ sigma)
+        // -- one test per bead; then (bead, trial bead) pairs of the survivors spread over the lanes
+#pragma unroll 1
+        for (int e0 = 0; e0 < items; e0 += 32) {
+            const int e = e0 + ln;
+            bool in = false;
+            float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (e < items) {
+                const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
+                s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
+                in = spheres_near(f, s, ct, Rt + 1.001f);
+                pairs += 1u;
+            }
+            const unsigned mask = __ballot_sync(FULL, in);
+            if (in) buf[__popc(mask & ((1u << ln) - 1u))] = s;
+            __syncwarp();
+            const int npair = __popc(mask) * nb;
+#pragma unroll 1
+            for (int t = ln; t < npair; t += 32) {
+                const int bi = NB ? t / (NB ? NB : 1) : div_nb(w, t);
+                const int b = t - bi * nb;
+                const float4 sb = buf[bi], tb = SM4[c4 + b];
+                const float r2 = r2_f32(f, sb.x - tb.x, sb.y - tb.y, sb.z - tb.z);
+                const bool moved = b >= b0;
+                ov |= moved && (r2 < f.lo);
+                amb |= moved && !(r2 > f.hi);
+                pairs += moved ? 1u : 0u;
+            }
+            __syncwarp(); // buf is rewritten by the next pass
+        }
+#else
 #pragma unroll 1
         for (int e = ln; e < items; e += 32) {
             const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
@@ -110,9 +152,10 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             }
             pairs += (unsigned)(nb - b0);
         }
+#endif
         if (cb + TEAM_LIST < nc) __syncwarp(); // the list is rewritten by the next chunk
     }
-    if (intra) { // dihedral: pairs (j, b), b >= b0, of the trial chain itself beyond the exclusion
+    if (active && intra) { // dihedral: pairs (j, b), b >= b0, of the trial chain itself beyond the exclusion
         const uchar2 *tab = W_ITAB(w);
 #pragma unroll 1
         for (int e = ln; e < w.npc; e += 32) {
@@ -129,12 +172,13 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
     // the chains of the earlier moves of the window, at their old position (F4, RAD) and at their trial position
     // (their w4 slot, rtw): bounding spheres first, lane j for the old and lane 8 + j for the new position of move j,
     // bead level only for the ones that are near
+    __syncthreads(); // the trial chains of the other warps (written before their own tests) are visible from here on
     unsigned oldb = 0, newb = 0;
-    {
+    if (active) {
         bool nr = false;
         const int j = ln & 7;
         if (ln < 16 && j < k) {
-            const int cj = win[j].ichain;
+            const int cj = wmeta[j] & 0xffff;
             const bool isnew = ln >= 8;
             const float4 cc = isnew ? SM4[w.w4 + nb * j + m] : SM4[f4 + cj * nb + m];
             const float rr = isnew ? rtw[j] : SMF[w.rad + cj];
@@ -146,30 +190,20 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             const int bit = __ffs(nm) - 1;
             nm &= nm - 1u;
             const int jj = bit & 7;
-            const int s4 = bit >= 8 ? w.w4 + nb * jj : f4 + win[jj].ichain * nb;
+            const int s4 = bit >= 8 ? w.w4 + nb * jj : f4 + (wmeta[jj] & 0xffff) * nb;
             bool o = false;
 #pragma unroll 1
-            for (int e = ln; e < nb; e += 32) {
-                const float4 s = SM4[s4 + e];
-                if (NB) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const float r2 = r2_f32(f, s.x - tr[b].x, s.y - tr[b].y, s.z - tr[b].z);
-                        const bool moved = b >= b0;
-                        o |= moved && (r2 < f.lo);
-                        amb |= moved && !(r2 > f.hi);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int b = b0; b < nb; ++b) {
-                        const float4 t = SM4[c4 + b];
-                        const float r2 = r2_f32(f, s.x - t.x, s.y - t.y, s.z - t.z);
-                        o |= (r2 < f.lo);
-                        amb |= !(r2 > f.hi);
-                    }
-                }
-                pairs += (unsigned)(nb - b0);
+            for (int t = ln; t < nb * nb; t += 32) { // (rare: the spheres of two moves of one window touch)
+                const int e = NB ? t / (NB ? NB : 1) : div_nb(w, t);
+                const int b = t - e * nb;
+                const float4 s = SM4[s4 + e], tb = SM4[c4 + b];
+                const float r2 = r2_f32(f, s.x - tb.x, s.y - tb.y, s.z - tb.z);
+                const bool moved = b >= b0;
+                o |= moved && (r2 < f.lo);
+                amb |= moved && !(r2 > f.hi);
+                pairs += moved ? 1u : 0u;
             }
+            o = __any_sync(FULL, o);
             if (bit >= 8) newb |= (o ? 1u : 0u) << jj; else oldb |= (o ? 1u : 0u) << jj;
         }
     }
@@ -186,10 +220,10 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
     const int nb = NB ? NB : w.nb;
     unsigned *res = reinterpret_cast<unsigned *>(smem) +
                     ((int)walker_smem_bytes(w.N, w.nb, T) + (int)window_smem_bytes(w.nb, NWARP)) / 4;
-    unsigned *plainw = res + 8;
-    unsigned *ucmw = res + 16;
     float *rtw = reinterpret_cast<float *>(res) + 24;
-    int *lst = reinterpret_cast<int *>(res) + 32 + TEAM_LIST * wid; // this warp's near list
+    int *meta = reinterpret_cast<int *>(res) + 32, *info = meta + T + 8;
+    int *lst = reinterpret_cast<int *>(res) + 48 + 2 * T + TEAM_LIST * wid; // this warp's near list
+    float4 *buf = reinterpret_cast<float4 *>(res + 48 + 2 * T + TEAM_LIST * NWARP) + 32 * wid;
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     for (int k = blockIdx.x; k < a.n_active; k += gridDim.x) {
         const int wi = a.ids ? a.ids[k] : k;
@@ -202,8 +236,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
         PropRec *ring = W_RING(w);
         for (int m0 = 0; m0 < a.nmoves; m0 += T) {
             const int nbatch = a.nmoves - m0 < T ? a.nmoves - m0 : T;
-            int my_type = -1;
-            bool my_plain = false; // a single-chain move with a well-formed proposal
+            int my_type = -1, my_meta = -1;
             if (w.lane < nbatch) {
                 PropRec *slot = ring + w.lane;
                 if (REPLAY) {
@@ -219,40 +252,40 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     slot->u_acc = pr.u_acc;
                     my_type = pr.type;
                 }
-                my_plain = (my_type == HANS_TRANS || my_type == HANS_ROT ||
-                            (my_type == HANS_DIH && nb >= 4 && slot->idx0 >= 3 && slot->idx0 <= nb - 1)) &&
-                           (unsigned)slot->ichain < (unsigned)w.nc;
+                // a single-chain move with a well-formed proposal
+                const bool plain = (my_type == HANS_TRANS || my_type == HANS_ROT ||
+                                    (my_type == HANS_DIH && nb >= 4 && slot->idx0 >= 3 && slot->idx0 <= nb - 1)) &&
+                                   (unsigned)slot->ichain < (unsigned)w.nc;
+                if (plain) my_meta = slot->ichain | ((slot->u_acc < 1.0) ? (1 << 30) : 0); // MCNS.py:372 with boltz = 1
             }
-            {
-                const unsigned pm = __ballot_sync(FULL, my_plain);
-                const unsigned um = __ballot_sync(FULL, w.lane < nbatch && ring[w.lane].u_acc < 1.0);
-                if (ln == 0) { plainw[wid] = pm; ucmw[wid] = um; }
+            meta[w.lane] = my_meta;
+            if (w.lane < 8) meta[T + w.lane] = -1;
+            __syncthreads();
+            {   // the run of plain moves of DISTINCT chains that starts at my move (at most NWARP), once per batch
+                int n = 0;
+                unsigned um = 0;
+                int ch[NWARP];
+                bool live = true;
+#pragma unroll
+                for (int j = 0; j < NWARP; ++j) {
+                    const int mj = meta[w.lane + j];
+                    ch[j] = mj & 0xffff;
+                    bool ok = live && mj >= 0;
+#pragma unroll
+                    for (int i = 0; i < j; ++i) ok = ok && (ch[i] != ch[j]);
+                    live = ok;
+                    n += ok ? 1 : 0;
+                    um |= (ok && (mj >> 30)) ? (1u << j) : 0u;
+                }
+                info[w.lane] = n | (int)(um << 8);
             }
             __syncthreads();
             int my_acc = 0, my_reason = 0;
             double my_boltz = 0.0;
             for (int q = 0; q < nbatch;) {
-                // the run of plain moves of distinct chains that starts at q (at most NWARP)
-                int nw;
-                unsigned ucm; // bit i = move q + i has u_acc < 1 (MCNS.py:372 with boltz = 1)
-                {
-                    const int qw = q >> 5;
-                    const unsigned lo = plainw[qw], hi = qw + 1 < NWARP ? plainw[qw + 1] : 0u;
-                    const unsigned bits = __funnelshift_r(lo, hi, q & 31); // bit i = move q + i is plain (0 past the batch)
-                    ucm = __funnelshift_r(ucmw[qw], qw + 1 < NWARP ? ucmw[qw + 1] : 0u, q & 31);
-                    nw = __ffs(~bits) - 1;
-                    if (nw < 0 || nw > NWARP) nw = NWARP;
-                    int ch[NWARP];
-#pragma unroll
-                    for (int i = 0; i < NWARP; ++i) ch[i] = i < nw ? ring[q + i].ichain : -1 - i;
-#pragma unroll
-                    for (int j = NWARP - 1; j >= 1; --j) {
-                        bool dup = false;
-#pragma unroll
-                        for (int i = 0; i < j; ++i) dup |= (ch[i] == ch[j]);
-                        if (dup && j < nw) nw = j;
-                    }
-                }
+                const int inf = info[q];
+                const int nw = inf & 0xff;          // moves of this window
+                const unsigned ucm = (unsigned)inf >> 8; // bit i = move q + i commits if it is accepted
                 if (nw == 0) { // box move or malformed proposal: the whole CTA on one move
                     const int type = ring[q].type;
                     int accepted, reason;
@@ -269,40 +302,45 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     ++q;
                     continue;
                 }
-                const PropRec *win = ring + q;
                 // ---- A1: warp k builds the trial chain of move k ---------------------------------
                 int ichain = 0, b0 = 0;
                 bool intra = false;
                 const int cnk = w.wc + 3 * nb * wid, c4k = w.w4 + nb * wid;
                 float Rt = 0.0f;
-                if (wid < nw) {
-                    ichain = win[wid].ichain;
-                    make_trial(w, win + wid, ln, 32, cnk, c4k, b0, intra);
-                    if (intra) __syncwarp();
+                const bool active = wid < nw;
+                if (active) {
+                    ichain = meta[q + wid] & 0xffff;
+                    make_trial(w, ring + q + wid, ln, 32, cnk, c4k, b0, intra);
+                    __syncwarp();
                     Rt = intra ? chain_radius(cnk, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
                     if (ln == 0) rtw[wid] = Rt;
                 }
-                __syncthreads();
-                // ---- A2: warp k tests it ----------------------------------------------------------
-                if (wid < nw) {
-                    const unsigned r = team_test<NB, NWARP>(w, f, win, lst, rtw, wid, ln, ichain, b0, intra, Rt, pairs);
-                    if (ln == 0) res[wid] = r;
+                // ---- A2: warp k tests it (one barrier inside, before the other warps' trial chains are read) ----
+                {
+                    const unsigned r = team_test<NB, NWARP>(w, f, meta + q, lst, buf, rtw, active, wid, ln, ichain, b0, intra, Rt, pairs);
+                    if (active && ln == 0) res[wid] = r;
                 }
                 __syncthreads();
-                // ---- B: settle in order (uniform over the CTA) -----------------------------------
+                // ---- B: settle in order (uniform over the CTA, branch free) ------------------------
                 unsigned committed = 0, accepted = 0;
                 int ndone = nw;
-#pragma unroll 1
-                for (int i = 0; i < nw; ++i) {
-                    const unsigned r = res[i];
-                    bool ov = (r & 1u) != 0u;
-                    if (!ov) {
-                        if (r & 2u) { ndone = i; break; } // a pair inside the band: float64 decides, serially
-                        ov = ((((r >> 16) & committed) | ((r >> 8) & ~committed)) & ((1u << i) - 1u)) != 0u;
-                    }
-                    if (!ov) {
-                        accepted |= 1u << i;
-                        committed |= ucm & (1u << i);
+                {
+                    unsigned r[8];
+                    *reinterpret_cast<uint4 *>(r) = *reinterpret_cast<const uint4 *>(res);
+                    if (NWARP > 4) *reinterpret_cast<uint4 *>(r + 4) = *reinterpret_cast<const uint4 *>(res + 4);
+                    bool live = true;
+#pragma unroll
+                    for (int i = 0; i < NWARP; ++i) {
+                        const unsigned ri = r[i];
+                        const bool in = live && i < nw;
+                        const bool certain = (ri & 1u) != 0u;
+                        const bool cut = in && !certain && (ri & 2u) != 0u; // a pair inside the band: float64 decides, serially
+                        ndone = cut ? i : ndone;
+                        live = live && !cut;
+                        const bool ov = certain || ((((ri >> 16) & committed) | ((ri >> 8) & ~committed)) & ((1u << i) - 1u)) != 0u;
+                        const unsigned bit = (in && !cut && !ov) ? (1u << i) : 0u;
+                        accepted |= bit;
+                        committed |= bit & ucm;
                     }
                 }
                 // ---- C: commit -----------------------------------------------------------------------
@@ -338,7 +376,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     o->accepted = my_acc; o->reason = my_reason; o->boltz = my_boltz;
                 }
             }
-            __syncthreads(); // the ring and the plain masks are rewritten by the next batch
+            __syncthreads(); // the ring, meta and info are rewritten by the next batch
         }
         store_walker<T>(w, a.H, a.R, wi);
         if (a.attempted) {

@@ -105,6 +105,10 @@ int hans_default_threads_per_walker(const hans_cfg *cfg);
 /* window size the warp-per-walker kernel uses for a shape when threads_per_walker = 0 (1 = one
  * move at a time, 8 = speculative windows); 0 = the shape runs on the cooperative kernel */
 int hans_default_window(const hans_cfg *cfg);
+/* warps per walker of the warp-per-move kernel (one CTA per walker, a window of consecutive chain moves
+ * of distinct chains in flight, one warp each) when threads_per_walker = 0 picks it for a shape
+ * (large walkers with many chains); 0 = the shape runs on one of the other kernels */
+int hans_default_team(const hans_cfg *cfg);
 
 /* ---- the fused hot path ---------------------------------------------------------------------
  * MC_run (NesSa/MCNS.py:276-392) for n_active walkers at once: sweeps * moves_per_sweep trial
@@ -121,8 +125,12 @@ int hans_default_window(const hans_cfg *cfg);
  *                     256 beads); 1 = one move at a time, 8 = speculative windows of up to 8
  *                     consecutive single-chain moves, settled in order (<= 128 beads; same
  *                     decisions and trajectory, bit for bit);
+ *                     24, 28: warp-per-move kernel for large chain systems (nbeads > 1): one CTA of
+ *                     4 / 8 warps per walker, up to 4 / 8 consecutive single-chain moves of distinct
+ *                     chains evaluated at once, one warp each, and settled in order (same decisions
+ *                     and trajectory, bit for bit); box moves are shared by the whole CTA;
  *                     0 = the measured default per shape: hans_default_window if non-zero, else
- *                     hans_default_threads_per_walker.
+ *                     hans_default_team if non-zero, else hans_default_threads_per_walker.
  *                     Every variant produces the same trajectory; the choice is speed only.
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,

@@ -79,6 +79,8 @@ def test_host_side_entry_points_and_validation():
     assert L.hans_default_threads_per_walker(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 64
     assert L.hans_default_window(C.byref(_lib.make_cfg(16, 12, [3, 32, 32, 16, 3, 3]))) == 1
     assert L.hans_default_window(C.byref(big)) == 0                                        # 128 chains: one CTA per walker
+    assert L.hans_default_team(C.byref(big)) == 8                                          # ... of 8 warps, one move each
+    assert L.hans_default_team(C.byref(cfg)) == 0 and L.hans_default_team(C.byref(_lib.make_cfg(32, 12, [3, 32, 32, 16, 3, 3]))) == 4
     assert L.hans_default_window(C.byref(_lib.make_cfg(16, 5, [1, 1, 1, 1, 1, 1]))) == 0   # nbeads = 5 is not instantiated
     assert L.hans_default_window(C.byref(_lib.make_cfg(200, 1, [1, 1, 0, 0, 1, 1]))) == 0  # 200 spheres
     assert L.hans_mc_run_batch_ws(None, None, None, None, None, 1, 1, None, 0.0, 0, 0, None, None, None, None, 0, None, 0, None) == -1
