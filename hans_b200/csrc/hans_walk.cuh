@@ -404,6 +404,9 @@ __device__ __forceinline__ bool make_trial(const WCtx &w, const PropRec *p, int 
 // the dilute regime: 540 -> ~60 per chain move).  This is the role hs_alkane's link cells play
 // (bypassed by the reference, MCNS.py:603), at chain granularity.
 // ---------------------------------------------------------------------------------------------
+#ifndef HANS_BEAD_PRUNE
+#define HANS_BEAD_PRUNE 1
+#endif
 __device__ __forceinline__ float chain_radius(int pos, int nb)
 {
     const int m = nb >> 1;
@@ -477,6 +480,46 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
         bool near = false;
         if (c < nc && c != ichain) near = spheres_near(f, SM4[f4 + c * nb + m], ct, Rt + SMF[w.rad + c] + 1.001f);
         const int items = near_list<T>(w, near, c, cb == 0) * nb;
+#if HANS_BEAD_PRUNE
+        if (T == 32 && w.N >= 32 && items <= 32) {
+            // few near chains (the usual case outside the dense regime; measured: with more than one pass of beads the
+            // unrolled loop below, six independent tests in flight per lane, is faster although it executes more tests).
+            // Bead level in two steps (one warp per walker): which beads of the near chains lie inside the trial
+            // chain's bounding sphere (+ sigma) -- one test per bead, the survivors' shadows go to a 32-entry buffer
+            // (the head of G4: the trial shadows of a box move, free during a chain move); then the (bead, trial bead)
+            // pairs of the survivors spread over the lanes.  Beads outside the sphere are further than sigma from every
+            // trial bead, so the decision is unchanged.
+            float4 *buf = SM4 + W_G4(w);
+#pragma unroll 1
+            for (int e0 = 0; e0 < items; e0 += 32) {
+                const int e = e0 + w.lane;
+                bool in = false;
+                float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (e < items) {
+                    const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
+                    s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
+                    in = spheres_near(f, s, ct, Rt + 1.001f);
+                    pairs += 1u;
+                }
+                const unsigned mask = __ballot_sync(FULL, in);
+                if (in) buf[__popc(mask & ((1u << w.lane) - 1u))] = s;
+                __syncwarp();
+                const int npair = __popc(mask) * nb;
+#pragma unroll 1
+                for (int t = w.lane; t < npair; t += 32) {
+                    const int bi = NB ? t / (NB ? NB : 1) : div_nb(w, t);
+                    const int b = t - bi * nb;
+                    const float4 sb = buf[bi], tb = SM4[c4 + b];
+                    const float r2 = r2_f32(f, sb.x - tb.x, sb.y - tb.y, sb.z - tb.z);
+                    const bool moved = b >= b0;
+                    ov |= moved && (r2 < f.lo);
+                    amb |= moved && !(r2 > f.hi);
+                    pairs += moved ? 1u : 0u;
+                }
+                __syncwarp(); // buf is rewritten by the next pass
+            }
+        } else
+#endif
         for (int e = w.lane; e < items; e += T) {
             const int ci = NB ? e / (NB ? NB : 1) : div_nb(w, e);
             const float4 s = SM4[f4 + lst[ci] * nb + (e - ci * nb)];
