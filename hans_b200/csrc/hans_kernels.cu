@@ -417,9 +417,10 @@ static bool team_applies(const hans_cfg *c, int nwarp)
     return c->nbeads > 1 && c->nchains >= 2 && team_smem_bytes(c, nwarp) <= 227 * 1024;
 }
 
-template <bool REPLAY> static int launch_team(const WalkArgs &a, int nwarp, cudaStream_t st)
+template <bool REPLAY> static int launch_team(WalkArgs a, int nwarp, cudaStream_t st)
 {
     const hans_cfg *c = &a.cfg;
+    a.team_res = (int)((walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp)) / 4);
     const size_t smem = team_smem_bytes(c, nwarp);
     const int cap = sm_count() * 8, grid = a.n_active < cap ? a.n_active : cap;
     int rc = HANS_OK;

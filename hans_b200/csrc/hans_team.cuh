@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
     const WCtx w = setup_ctx_g<T, 1>(a.cfg, NWARP, team_tail_bytes(NWARP));
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const int nb = NB ? NB : w.nb;
-    unsigned *res = reinterpret_cast<unsigned *>(smem) +
-                    ((int)walker_smem_bytes(w.N, w.nb, T) + (int)window_smem_bytes(w.nb, NWARP)) / 4;
+    unsigned *res = reinterpret_cast<unsigned *>(smem) + a.team_res; // (walker + window area) / 4, from the launcher
     float *rtw = reinterpret_cast<float *>(res) + 24;
     int *meta = reinterpret_cast<int *>(res) + 32, *info = meta + T + 8;
     int *lst = reinterpret_cast<int *>(res) + 48 + 2 * T + TEAM_LIST * wid; // this warp's near list
@@ -328,19 +327,31 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     unsigned r[8];
                     *reinterpret_cast<uint4 *>(r) = *reinterpret_cast<const uint4 *>(res);
                     if (NWARP > 4) *reinterpret_cast<uint4 *>(r + 4) = *reinterpret_cast<const uint4 *>(res + 4);
-                    bool live = true;
+                    unsigned cert = 0, other = 0; // per move: certain overlap; anything else (band, earlier moves)
 #pragma unroll
                     for (int i = 0; i < NWARP; ++i) {
-                        const unsigned ri = r[i];
-                        const bool in = live && i < nw;
-                        const bool certain = (ri & 1u) != 0u;
-                        const bool cut = in && !certain && (ri & 2u) != 0u; // a pair inside the band: float64 decides, serially
-                        ndone = cut ? i : ndone;
-                        live = live && !cut;
-                        const bool ov = certain || ((((ri >> 16) & committed) | ((ri >> 8) & ~committed)) & ((1u << i) - 1u)) != 0u;
-                        const unsigned bit = (in && !cut && !ov) ? (1u << i) : 0u;
-                        accepted |= bit;
-                        committed |= bit & ucm;
+                        const unsigned ri = i < nw ? r[i] : 0u;
+                        cert |= (ri & 1u) << i;
+                        other |= ri >> 1;
+                    }
+                    if (other == 0u) { // the usual case: no move of the window is near an earlier one's chain
+                        accepted = ~cert & ((1u << nw) - 1u);
+                        committed = accepted & ucm;
+                    } else {
+                        bool live = true;
+#pragma unroll
+                        for (int i = 0; i < NWARP; ++i) {
+                            const unsigned ri = r[i];
+                            const bool in = live && i < nw;
+                            const bool certain = (ri & 1u) != 0u;
+                            const bool cut = in && !certain && (ri & 2u) != 0u; // a pair inside the band: float64 decides, serially
+                            ndone = cut ? i : ndone;
+                            live = live && !cut;
+                            const bool ov = certain || ((((ri >> 16) & committed) | ((ri >> 8) & ~committed)) & ((1u << i) - 1u)) != 0u;
+                            const unsigned bit = (in && !cut && !ov) ? (1u << i) : 0u;
+                            accepted |= bit;
+                            committed |= bit & ucm;
+                        }
                     }
                 }
                 // ---- C: commit -----------------------------------------------------------------------

@@ -1030,6 +1030,7 @@ struct WalkArgs {
     const hans_proposal *props; // replay
     hans_decision *out;
     int mode;
+    int team_res; // warp-per-move kernel: int offset of its tail area in shared memory (set by the launcher)
 };
 
 template <int T, bool REPLAY>
