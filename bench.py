@@ -429,6 +429,7 @@ def run_b200(args):
                          "kernel_share_of_step": kernel_ms / (ms / args.steps),
                          "algorithmic_pair_tests_per_launch": pairs_per_launch, "flop_per_pair_test": FLOP_PER_PAIR,
                          "executed_pair_tests_per_launch": executed_pairs, "achieved_executed": achieved_exec,
+                         "frac_executed": achieved_exec / ffma_peak if ffma_peak else None,
                          "peak_source": "FFMA issue-rate probe (hans_ffma_peak) run in this process; "
                                         "MEASURED_PEAKS.json holds no FP32 figure"},
             "cpu_baseline": cpu,
