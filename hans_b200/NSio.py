@@ -1,12 +1,13 @@
 """Mirror of the reference's ``NesSa.NSio``: stdin `key = value` input, restart file, extxyz
 trajectory (all file:line citations into /root/reference/NesSa/NSio.py unless noted).
 
-restart.hdf5: written with h5py when it is importable (schema of NSio.py:69-111: root attributes =
-every parameter + prev_iters + step sizes, one group per walker `walker_{rank}_{i:04d}` with
-`coordinates (N,3) f8` and `unitcell (3,3) f8`).  h5py is NOT installed in this image, so the same
-logical content is then stored as a numpy .npz container next to the requested name
-(`restart.hdf5` -> `restart.hdf5.npz`, keys `attr/<name>`, `<group>/coordinates`,
-`<group>/unitcell`); `open_restart` reads either.  This is a documented gap.
+restart.hdf5: schema of NSio.py:69-111 -- root attributes = every parameter + prev_iters + step
+sizes, one group per walker `walker_{rank}_{i:04d}` with `coordinates (N,3) f8` and
+`unitcell (3,3) f8`.  Written with h5py when it is importable; h5py is NOT installed in this image,
+so the file is then written by `hans_b200/h5min.py`, a dependency-free writer of the HDF5 subset the
+schema needs (superblock 0, old-style groups, contiguous float64 datasets, scalar / 1-d int64,
+float64 and fixed-length string attributes).  `open_restart` reads h5py-written files through h5py,
+h5min-written files through h5min, and the `.npz` container earlier versions of this package wrote.
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ import sys
 
 import numpy as np
 
+from . import h5min
 from .atoms import Atoms, read_extxyz, write_extxyz
 
 try:  # pragma: no cover - not available in the build image
@@ -95,17 +97,12 @@ def save_restart(filename: str, attrs: dict, walkers: dict) -> str:
                 grp.create_dataset("coordinates", data=np.asarray(coords, dtype=np.float64))
                 grp.create_dataset("unitcell", data=np.asarray(cell, dtype=np.float64))
         return filename
-    out = {}
-    for k, v in attrs.items():
-        out["attr/" + k] = np.asarray(v)
-    for g, (coords, cell) in walkers.items():
-        out[g + "/coordinates"] = np.asarray(coords, dtype=np.float64)
-        out[g + "/unitcell"] = np.asarray(cell, dtype=np.float64)
-    path = _npz_name(filename)
-    tmp = path + ".tmp.npz"
-    np.savez(tmp, **out)
-    os.replace(tmp, path)
-    return path
+    tmp = filename + ".tmp"
+    h5min.write(tmp, attrs, {g: {"coordinates": np.asarray(coords, dtype=np.float64).reshape(-1, 3),
+                                  "unitcell": np.asarray(cell, dtype=np.float64).reshape(3, 3)}
+                             for g, (coords, cell) in walkers.items()})
+    os.replace(tmp, filename)
+    return filename
 
 
 def open_restart(filename: str):
@@ -118,7 +115,10 @@ def open_restart(filename: str):
             for g in f:
                 walkers[g] = (f[g]["coordinates"][:], f[g]["unitcell"][:])
         return attrs, walkers
-    path = _npz_name(filename)
+    if os.path.exists(filename) and h5min.is_hdf5(filename):
+        attrs, groups = h5min.read(filename)
+        return attrs, {g: (d["coordinates"], d["unitcell"]) for g, d in groups.items()}
+    path = _npz_name(filename)  # the container written before h5min existed
     if not os.path.exists(path):
         raise FileNotFoundError(f"no restart file {filename} (or {path})")
     attrs, walkers = {}, {}

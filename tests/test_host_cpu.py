@@ -157,3 +157,143 @@ def test_restart_container_and_cleanup(tmp_path, monkeypatch):
     assert len(open("volumes.txt").read().splitlines()) == 251
     from hans_b200.atoms import read_extxyz
     assert len(read_extxyz("traj.extxyz", ":")) == 2
+
+
+def test_h5min_round_trip_and_structure(tmp_path):
+    """restart.hdf5 without h5py: the dependency-free HDF5 writer (hans_b200/h5min.py).  Round trip through its
+    own reader, and the structural rules libhdf5's reader enforces: end-of-file address = file size, nodes at
+    full size, names sorted, group B-tree keys bounding the names of child i as (key[i], key[i+1]], siblings
+    linked, heap free list = 1 (H5HL_FREE_NULL)."""
+    import struct
+    from hans_b200 import h5min
+    rng = np.random.default_rng(3)
+    ngroups = 600  # 75 symbol table nodes -> 3 leaf-level B-tree nodes -> a second B-tree level
+    groups = {f"walker_{i % 3}_{i // 3 + 1:04d}": {"coordinates": rng.normal(size=(12, 3)), "unitcell": rng.normal(size=(3, 3))}
+              for i in range(ngroups)}
+    attrs = {"nchains": 16, "bondlength": 0.4, "iterations": "800000", "directory": "NeSa_16_6mer.20.40.1",
+             "move_ratio": np.array([3.0, 48, 32, 0, 3, 3]), "profile": False, "prev_iters": 50000, "time": float("inf"),
+             "seed": 2 ** 40 + 7, "empty": "", "unicode": "σ = 1"}
+    fn = str(tmp_path / "restart.hdf5")
+    h5min.write(fn, attrs, groups)
+    assert h5min.is_hdf5(fn)
+    a2, g2 = h5min.read(fn)
+    assert set(a2) == set(attrs)
+    assert a2["nchains"] == 16 and a2["bondlength"] == 0.4 and a2["iterations"] == "800000" and a2["seed"] == 2 ** 40 + 7
+    assert a2["profile"] == 0 and a2["time"] == float("inf") and a2["empty"] == "" and a2["unicode"] == "σ = 1"
+    assert list(a2["move_ratio"]) == [3, 48, 32, 0, 3, 3] and a2["directory"] == attrs["directory"]
+    assert sorted(g2) == sorted(groups)
+    for g in groups:
+        for d in ("coordinates", "unitcell"):
+            assert g2[g][d].dtype == np.float64 and np.array_equal(g2[g][d], groups[g][d])
+    # ---- structure ----
+    raw = open(fn, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    leaf_k, int_k = struct.unpack_from("<HH", raw, 16)
+    assert (leaf_k, int_k) == (4, 16)
+    base, free, eof, drv = struct.unpack_from("<QQQQ", raw, 24)
+    assert base == 0 and eof == len(raw) and free == drv == 0xFFFFFFFFFFFFFFFF
+    name_off, root_hdr, cache, _ = struct.unpack_from("<QQII", raw, 56)
+    bt_c, heap_c = struct.unpack_from("<QQ", raw, 80)
+    r = h5min._Reader(raw)
+    stab = [m for t, m in r.messages(root_hdr) if t == 0x0011][0]
+    assert cache == 1 and struct.unpack("<QQ", stab[:16]) == (bt_c, heap_c) and name_off == 0
+    assert raw[heap_c:heap_c + 4] == b"HEAP"
+    seg_size, free_head, seg = struct.unpack_from("<QQQ", raw, heap_c + 8)
+    assert free_head == 1 and seg % 8 == 0 and seg_size % 8 == 0 and raw[seg] == 0
+
+    def name(off):
+        return r.heap_name(heap_c, off).encode()
+
+    levels = {}
+
+    def walk(addr, lo, hi):
+        """every name below `addr` must lie in (lo, hi]"""
+        assert addr % 8 == 0
+        if raw[addr:addr + 4] == b"SNOD":
+            assert addr + 8 + 40 * 8 <= len(raw)
+            n = struct.unpack_from("<H", raw, addr + 6)[0]
+            names = [name(struct.unpack_from("<Q", raw, addr + 8 + 40 * i)[0]) for i in range(n)]
+            assert 1 <= n <= 8 and names == sorted(names) and lo < names[0] and names[-1] <= hi
+            for i in range(n):  # sub-groups carry their B-tree / heap in the scratch pad
+                _, hdr, ctype, _ = struct.unpack_from("<QQII", raw, addr + 8 + 40 * i)
+                assert ctype == 1
+                sub = [m for t, m in r.messages(hdr) if t == 0x0011][0]
+                assert raw[addr + 8 + 40 * i + 24:addr + 8 + 40 * i + 40] == sub[:16]
+            return n
+        assert raw[addr:addr + 4] == b"TREE" and addr + 24 + 8 * 32 + 8 * 33 <= len(raw)
+        ntype, lvl, used, left, right = struct.unpack_from("<BBHQQ", raw, addr + 4)
+        assert ntype == 0 and 1 <= used <= 32
+        levels.setdefault(lvl, []).append((addr, left, right))
+        keys = [name(struct.unpack_from("<Q", raw, addr + 24 + 16 * i)[0]) for i in range(used + 1)]
+        assert keys[0] == lo and keys[-1] == hi and keys == sorted(keys)
+        total = 0
+        for i in range(used):
+            child = struct.unpack_from("<Q", raw, addr + 24 + 8 + 16 * i)[0]
+            total += walk(child, keys[i], keys[i + 1])
+        return total
+
+    root_used = struct.unpack_from("<H", raw, bt_c + 6)[0]
+    top_key = name(struct.unpack_from("<Q", raw, bt_c + 24 + 16 * root_used)[0])
+    assert walk(bt_c, b"", top_key) == ngroups and top_key == max(g.encode() for g in groups)
+    assert sorted(levels) == [0, 1] and len(levels[0]) == 3 and len(levels[1]) == 1
+    undef = 0xFFFFFFFFFFFFFFFF
+    for lvl, nodes in levels.items():  # siblings, left to right
+        assert nodes[0][1] == undef and nodes[-1][2] == undef
+        for (a0, _, r0), (a1, l1, _) in zip(nodes, nodes[1:]):
+            assert r0 == a1 and l1 == a0
+    # a dataset header: dataspace, datatype (IEEE float64 little endian), fill value, contiguous layout
+    hdr = r.links(r.links(root_hdr)["walker_0_0001"])["coordinates"]
+    ms = dict(r.messages(hdr))
+    assert ms[0x0003][:20] == bytes.fromhex("11203f00080000000000400034" "0b0034ff030000")
+    assert ms[0x0001][:24] == struct.pack("<BBB5xQQ", 1, 2, 0, 12, 3) and ms[0x0008][:2] == b"\x03\x01"
+    addr, size = struct.unpack_from("<QQ", ms[0x0008], 2)
+    assert size == 12 * 3 * 8 and addr % 8 == 0 and addr + size <= len(raw)
+    # an empty group and an empty file are still well formed
+    h5min.write(fn, {}, {"lonely": {}})
+    a3, g3 = h5min.read(fn)
+    assert a3 == {} and g3 == {"lonely": {}}
+
+
+def test_h5min_file_opens_with_h5py(tmp_path):
+    """Cross-check against libhdf5 where h5py exists (it is absent from the build image, so this is skipped there)."""
+    h5py = pytest.importorskip("h5py")
+    from hans_b200 import h5min
+    rng = np.random.default_rng(4)
+    groups = {f"walker_0_{i + 1:04d}": {"coordinates": rng.normal(size=(6, 3)), "unitcell": rng.normal(size=(3, 3))} for i in range(300)}
+    fn = str(tmp_path / "restart.hdf5")
+    h5min.write(fn, {"nchains": 16, "bondlength": 0.4, "iterations": "800000", "move_ratio": np.arange(6.0)}, groups)
+    with h5py.File(fn, "r") as f:
+        assert sorted(f) == sorted(groups) and f.attrs["nchains"] == 16 and f.attrs["bondlength"] == 0.4
+        assert list(f.attrs["move_ratio"]) == list(range(6))
+        assert np.array_equal(f["walker_0_0007"]["unitcell"][:], groups["walker_0_0007"]["unitcell"])
+
+
+def test_h5min_reader_on_a_libhdf5_written_file():
+    """The one libhdf5-written file in the image: scipy's MATLAB v7.3 test file (superblock 0 behind a 512-byte user
+    block, old-style root group, one contiguous float64 dataset with a string attribute).  The reader shares every
+    structure with the writer (superblock, local heap, B-tree keys, symbol table node, version 1 object header,
+    dataspace / datatype / attribute messages), so parsing it pins the writer's understanding of the format."""
+    import scipy.io
+    fn = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(fn):
+        pytest.skip("scipy's test data is not installed")
+    import struct
+    from hans_b200 import h5min
+    raw = open(fn, "rb").read()
+    r = h5min._Reader(raw)
+    links = r.links(r.root_header)
+    assert list(links) == ["testdouble"]
+    a = r.dataset(links["testdouble"])
+    assert a.shape == (9, 1) and np.allclose(a[:, 0], np.arange(9) * np.pi / 4)
+    assert r.attributes(links["testdouble"]) == {"MATLAB_class": "double"}
+    # what libhdf5 wrote where the writer has to make the same choices
+    d = r.d
+    bt, heap = struct.unpack_from("<QQ", d, 80)
+    used = struct.unpack_from("<H", d, bt + 6)[0]
+    k0, child, k1 = struct.unpack_from("<QQQ", d, bt + 24)
+    assert used == 1 and r.heap_name(heap, k0) == "" and r.heap_name(heap, k1) == "testdouble"     # (key[i], key[i+1]]
+    free_head = struct.unpack_from("<Q", d, heap + 16)[0]
+    seg = struct.unpack_from("<Q", d, heap + 24)[0]
+    assert struct.unpack_from("<Q", d, seg + free_head)[0] == 1                                     # H5HL_FREE_NULL ends the free list
+    ms = dict(r.messages(links["testdouble"]))
+    assert ms[0x0003][:20] == h5min._dt_f64() and ms[0x0001][:24] == h5min._dataspace((9, 1))
