@@ -297,3 +297,53 @@ def test_h5min_reader_on_a_libhdf5_written_file():
     assert struct.unpack_from("<Q", d, seg + free_head)[0] == 1                                     # H5HL_FREE_NULL ends the free list
     ms = dict(r.messages(links["testdouble"]))
     assert ms[0x0003][:20] == h5min._dt_f64() and ms[0x0001][:24] == h5min._dataspace((9, 1))
+
+
+def test_window_settle_rule_equals_serial_order():
+    """The rule the warp-per-move kernel settles a window with (hans_b200/csrc/hans_team.cuh), on a toy system where
+    it can be enumerated: rods on a ring, a move shifts one rod, a move is accepted iff the shifted rod overlaps no
+    other rod.  Window = consecutive moves of DISTINCT rods; every move is evaluated against the state at the START of
+    the window, split into `base` (rods no earlier move of the window touches), `old[j]` / `new[j]` (the rod of the
+    earlier move j at its old / trial position); then in order: overlap_k = base_k or any_j<k (committed_j ? new_kj :
+    old_kj).  Must equal one-move-at-a-time evaluation, for every window length."""
+    rng = np.random.default_rng(11)
+    L, n = 40.0, 12
+
+    def ov(a, b):
+        d = abs(a - b) % L
+        return min(d, L - d) < 1.0
+
+    for W in (2, 4, 8):
+        x = np.arange(n) * (L / n) + rng.uniform(-0.5, 0.5, n)
+        moves = [(int(rng.integers(n)), float(rng.normal(scale=2.5))) for _ in range(4000)]
+        xs = x.copy()  # serial reference
+        serial = []
+        for c, dx in moves:
+            t = (xs[c] + dx) % L
+            ok = not any(ov(t, xs[j]) for j in range(n) if j != c)
+            serial.append(ok)
+            if ok:
+                xs[c] = t
+        xw, got, q, nwin = x.copy(), [], 0, 0
+        while q < len(moves):
+            nw = 1
+            while nw < W and q + nw < len(moves) and moves[q + nw][0] not in [m[0] for m in moves[q:q + nw]]:
+                nw += 1
+            win = moves[q:q + nw]
+            trial = [(xw[c] + dx) % L for c, dx in win]
+            committed = []
+            for k, (c, _) in enumerate(win):
+                early = [m[0] for m in win[:k]]
+                base = any(ov(trial[k], xw[j]) for j in range(n) if j != c and j not in early)
+                old = [ov(trial[k], xw[cj]) for cj in early]
+                new = [ov(trial[k], trial[j]) for j in range(k)]
+                over = base or any(new[j] if committed[j] else old[j] for j in range(k))
+                committed.append(not over)
+            for k, (c, _) in enumerate(win):
+                if committed[k]:
+                    xw[c] = trial[k]
+            got += committed
+            q += nw
+            nwin += 1
+        assert got == serial and np.array_equal(xw, xs)
+        assert 0.2 < np.mean(serial) < 0.95 and nwin < len(moves) / min(W, 3) * 1.6
