@@ -545,6 +545,17 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
     return HANS_OK;
 }
 
+static int gen_launch(const hans_cfg *cfg, const uint64_t *d_ctr, uint64_t ctr_off, const int32_t *d_ids, int n_active,
+                      int nmoves, uint64_t seed, uint32_t gid_base, hans_proposal *d_props, cudaStream_t st)
+{
+    const size_t total = (size_t)n_active * (size_t)nmoves;
+    const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 64;
+    gen_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(*cfg, (const unsigned long long *)d_ctr, ctr_off, d_ids,
+                                                                   n_active, nmoves, seed, gid_base, d_props);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
 int hans_gen_proposals(const hans_cfg *cfg, const uint64_t *d_ctr, const int32_t *d_ids, int n_active, int nmoves,
                        uint64_t seed, uint32_t gid_base, hans_proposal *d_props, void *stream)
 {
@@ -553,12 +564,30 @@ int hans_gen_proposals(const hans_cfg *cfg, const uint64_t *d_ctr, const int32_t
     if (!d_ctr || !d_props) return fail(HANS_EINVAL, "d_ctr and d_props are required");
     if (n_active < 0 || nmoves < 0) return fail(HANS_EINVAL, "negative count");
     if (n_active == 0 || nmoves == 0) return HANS_OK;
-    const size_t total = (size_t)n_active * (size_t)nmoves;
-    const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 64;
-    gen_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-        *cfg, (const unsigned long long *)d_ctr, d_ids, n_active, nmoves, seed, gid_base, d_props);
-    CK(cudaGetLastError());
-    return HANS_OK;
+    return gen_launch(cfg, d_ctr, 0, d_ids, n_active, nmoves, seed, gid_base, d_props, (cudaStream_t)stream);
+}
+
+// How hans_mc_run_batch_ws cuts a walk of `total` moves: the workspace holds the whole walk -> one generate + one
+// walk; it holds less -> chunks of what fits, generated and walked in turn through the one buffer; no workspace ->
+// generation inside the walk kernel.  (Measured and dropped: cutting a walk that fits into four chunks generated on a
+// side stream while the previous chunk is walked hides the generator -- 5 % of a C2 step -- but every chunk reloads its
+// walker and has its own tail of late CTAs: C2 1 465 -> 1 294, C3 559 -> 520, C5 373 -> 364 M moves/s.)
+struct WsPlan { int chunk; int nchunks; };
+static WsPlan ws_plan(int n_active, int total, bool have_ws, uint64_t workspace_bytes)
+{
+    WsPlan p = {0, 0};
+    if (!have_ws || n_active <= 0 || total <= 0) return p;
+    const uint64_t per_move = (uint64_t)n_active * sizeof(hans_proposal);
+    const uint64_t chunk = workspace_bytes / per_move;
+    p.chunk = chunk >= (uint64_t)total ? total : (int)(chunk & ~(uint64_t)31); // a multiple of 32: the kernels take proposals 32 at a time
+    p.nchunks = p.chunk ? (total + p.chunk - 1) / p.chunk : 0;
+    return p;
+}
+
+int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes)
+{
+    const WsPlan p = ws_plan(n_active, nmoves, have_workspace != 0, workspace_bytes);
+    return p.nchunks ? 2 * p.nchunks : 1;
 }
 
 int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr, const int32_t *d_ids,
@@ -581,19 +610,19 @@ int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t
     a.attempted = (unsigned long long *)d_attempted; a.accepted = (unsigned long long *)d_accepted;
     a.vol = d_vol; a.pair_tests = (unsigned long long *)d_pair_tests; a.mode = HANS_MODE_FUSED;
     cudaStream_t st = (cudaStream_t)stream;
-    // moves per chunk the workspace holds (a multiple of 32: the kernels take proposals 32 at a time)
-    const uint64_t per_move = (uint64_t)n_active * sizeof(hans_proposal);
     const int total = a.nmoves;
-    uint64_t chunk = d_workspace ? workspace_bytes / per_move : 0;
-    if (chunk < (uint64_t)total) chunk &= ~(uint64_t)31; else chunk = (uint64_t)total;
-    if (chunk == 0) return launch_walk(cfg, a, false, threads_per_walker, st); // no workspace: generate in the kernel
-    for (int m0 = 0; m0 < total; m0 += (int)chunk) {
-        const int n = total - m0 < (int)chunk ? total - m0 : (int)chunk;
-        rc = hans_gen_proposals(cfg, d_ctr, d_ids, n_active, n, seed, gid_base, (hans_proposal *)d_workspace, stream);
+    const WsPlan plan = ws_plan(n_active, total, d_workspace != nullptr, workspace_bytes);
+    if (plan.nchunks == 0) return launch_walk(cfg, a, false, threads_per_walker, st); // no workspace: generate in the kernel
+    hans_proposal *ws = (hans_proposal *)d_workspace;
+    const int chunk = plan.chunk;
+    for (int m0 = 0; m0 < total; m0 += chunk) {
+        const int n = total - m0 < chunk ? total - m0 : chunk;
+        rc = gen_launch(cfg, d_ctr, 0, d_ids, n_active, n, seed, gid_base, ws, st);
         if (rc) return rc;
         a.nmoves = n;
-        a.props = (const hans_proposal *)d_workspace;
+        a.props = ws;
         a.out = nullptr;
+        a.ctr_add = (unsigned long long)n;
         rc = launch_walk(cfg, a, true, threads_per_walker, st); // advances d_ctr by n
         if (rc) return rc;
     }
@@ -622,7 +651,7 @@ int hans_replay(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_
     WalkArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = *cfg; a.H = d_H; a.R = d_R; a.ids = d_ids; a.n_active = n_active; a.nmoves = nmoves;
-    a.limit = volume_limit; a.props = d_props; a.out = d_out; a.mode = mode;
+    a.limit = volume_limit; a.props = d_props; a.out = d_out; a.mode = mode; a.ctr_add = (unsigned long long)nmoves;
     return launch_walk(cfg, a, true, threads_per_walker, (cudaStream_t)stream);
 }
 

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
         }
         if (w.lane == 0) {
             if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
-            else if (a.ctr) a.ctr[wi] += (unsigned long long)a.nmoves; // proposals came from hans_gen_proposals
+            else if (a.ctr) a.ctr[wi] += a.ctr_add; // proposals came from hans_gen_proposals
             if (a.vol) a.vol[wi] = fabs(det3(smem + W_SH(w)));
         }
         if (a.pair_tests) {

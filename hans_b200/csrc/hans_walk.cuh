@@ -1031,6 +1031,7 @@ struct WalkArgs {
     hans_decision *out;
     int mode;
     int team_res; // warp-per-move kernel: int offset of its tail area in shared memory (set by the launcher)
+    unsigned long long ctr_add; // proposals from memory: what the walk adds to the walkers' proposal counters
 };
 
 template <int T, bool REPLAY>
@@ -1115,7 +1116,7 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
             }
             if (w.lane == 0) {
                 if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
-                else if (a.ctr) a.ctr[wi] += (unsigned long long)a.nmoves; // proposals came from hans_gen_proposals
+                else if (a.ctr) a.ctr[wi] += a.ctr_add; // proposals came from hans_gen_proposals
                 if (a.vol) a.vol[wi] = fabs(det3(smem + W_SH(w)));
             }
             if (a.pair_tests) {
@@ -1134,17 +1135,17 @@ __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a
 // on the state, so this throughput-bound part (Philox, Box-Muller, quaternions) runs at full
 // occupancy here instead of on the latency-bound critical path -- and outside the instruction-cache
 // footprint -- of the walk kernels, which then read 64 bytes per move from HBM.
-// props[k][m] = proposal number ctr[walker k] + m of walker k (same stream as the fused kernels).
+// props[k][m] = proposal number ctr[walker k] + ctr_off + m of walker k (same stream as the fused kernels).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gen_kernel(const hans_cfg cfg, const unsigned long long *ctr, const int32_t *ids,
-                                                  int n_active, int nmoves, unsigned long long seed, uint32_t gid_base,
-                                                  hans_proposal *props)
+__global__ void __launch_bounds__(256) gen_kernel(const hans_cfg cfg, const unsigned long long *ctr, unsigned long long ctr_off,
+                                                  const int32_t *ids, int n_active, int nmoves, unsigned long long seed,
+                                                  uint32_t gid_base, hans_proposal *props)
 {
     const size_t total = (size_t)n_active * (size_t)nmoves;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(t / (size_t)nmoves), m = (int)(t - (size_t)k * nmoves);
         const int wi = ids ? ids[k] : k;
-        const Prop pr = gen_proposal(&cfg, seed, gid_base + (uint32_t)wi, ctr[wi] + (unsigned long long)m);
+        const Prop pr = gen_proposal(&cfg, seed, gid_base + (uint32_t)wi, ctr[wi] + ctr_off + (unsigned long long)m);
         PropRec r;
         r.type = pr.type; r.ichain = pr.ichain; r.idx0 = pr.idx0; r.idx1 = pr.idx1;
         r.p[0] = pr.p[0]; r.p[1] = pr.p[1]; r.p[2] = pr.p[2]; r.p[3] = pr.p[3];

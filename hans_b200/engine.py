@@ -184,14 +184,12 @@ class WalkerPool:
         ws_bytes = min(need, self.workspace_bytes)
         if ws_bytes and (self._ws is None or self._ws.numel() < ws_bytes):
             self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        chunk = ws_bytes // max(n * PROPOSAL_DTYPE.itemsize, 1)
-        chunk = nmoves if chunk >= nmoves else chunk & ~31
         check(lib.hans_mc_run_batch_ws(C.byref(c), self.H.data_ptr(), self.R.data_ptr(), self.ctr.data_ptr(), _ptr(d_ids),
                                        n, int(sweeps), _ptr(d_volume_limit), float(volume_limit), self.seed, self.gid_base,
                                        _ptr(att), _ptr(acc), self.vol.data_ptr(),
                                        self.pair_tests.data_ptr() if count_pairs else None, self.tpw,
                                        _ptr(self._ws) if ws_bytes else None, int(ws_bytes), _stream()))
-        self.launches += 1 if chunk == 0 else 2 * -(-nmoves // chunk)  # (generate + walk) per chunk
+        self.launches += lib.hans_mc_run_launches(n, nmoves, 1 if ws_bytes else 0, int(ws_bytes))  # (generate + walk) per chunk
         return att, acc
 
     def replay(self, ids, proposals: np.ndarray, volume_limit: float = DBL_MAX, mode: int = MODE_FUSED) -> np.ndarray:

@@ -143,7 +143,8 @@ int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d
  * hans_gen_proposals (throughput-bound: Philox, Box-Muller, quaternions) fills d_workspace at full
  * occupancy and the latency-bound walk kernel reads 64 bytes per move instead of computing them on
  * its critical path.  Same trajectory, bit for bit.  The workspace holds n_active * 64 bytes per
- * move; if it is smaller than the walk, the walk is cut into chunks (generate, walk, generate, ...);
+ * move; if it is smaller than the walk, the walk is cut into chunks of what fits (generate, walk,
+ * generate, ...);
  * d_workspace = NULL falls back to generation inside the walk kernel (= hans_mc_run_batch). */
 int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
                          const int32_t *d_ids, int n_active, int sweeps,
@@ -151,6 +152,9 @@ int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t
                          uint32_t gid_base, uint64_t *d_attempted, uint64_t *d_accepted,
                          double *d_vol, uint64_t *d_pair_tests, int threads_per_walker,
                          void *d_workspace, uint64_t workspace_bytes, void *stream);
+
+/* kernel launches hans_mc_run_batch_ws makes for a walk of nmoves moves per walker (for launch accounting) */
+int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes);
 
 /* d_props[k][m] = proposal number d_ctr[walker k] + m of walker k = d_ids[k], m < nmoves: exactly
  * the proposals hans_mc_run_batch would draw (four Philox4x32-10 blocks per move

@@ -109,3 +109,15 @@ def test_no_product_module_touches_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r"CPU checker", "", text).lower() or f in (), (
                     f"{f} mentions the oracle")
+
+
+def test_workspace_plan_launch_count():
+    """hans_mc_run_launches mirrors how hans_mc_run_batch_ws cuts a walk (include/hans_b200.h)."""
+    from hans_b200 import _lib
+    L = _lib.lib
+    per_move = 1024 * 64
+    assert L.hans_mc_run_launches(1024, 2840, 1, 2840 * per_move) == 2        # whole walk fits: generate, walk
+    assert L.hans_mc_run_launches(1024, 2840, 1, 10 ** 12) == 2
+    assert L.hans_mc_run_launches(1024, 2840, 1, 1000 * per_move) == 2 * 3    # 992 moves fit: generate, walk, three times
+    assert L.hans_mc_run_launches(1024, 2840, 0, 0) == 1                       # no workspace: generation inside the walk kernel
+    assert L.hans_mc_run_launches(8, 87, 1, 8 * 64 * 40) == 2 * 3              # 32 of 87 moves fit
