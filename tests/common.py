@@ -15,6 +15,7 @@ SHAPES = {
     "t3": (11, 3, [2, 20, 20, 0, 3, 3]),       # nbeads the warp-per-walker kernel is not instantiated for, odd nchains
     "h15": (15, 6, [3, 48, 32, 10, 3, 3]),     # odd number of chains (round robin over chain pairs), dihedrals on
     "p7": (9, 7, [2, 20, 20, 10, 3, 3]),       # nbeads = 7: cooperative kernel, runtime nbeads, intra-chain pairs
+    "d140": (140, 2, [2, 60, 40, 0, 3, 3]),    # more than 128 chains: two chunks of chain spheres in the warp-per-move kernel
     "tiny": (6, 2, [1, 18, 12, 0, 3, 3]),    # fewer beads than lanes: several lanes share a bead row in box moves
     "tiny1": (5, 1, [1, 15, 0, 0, 3, 3]),
 }

@@ -255,7 +255,8 @@ def test_replay_invalid_and_edge(eng, oracle):
                                                ("d40", 0, 6), ("d40", 32, 6), ("d40", 64, 6), ("t3", 0, 8), ("t3", 64, 8),
                                                ("h15", 0, 6), ("h15", 8, 6), ("h15", 128, 6), ("p7", 0, 6), ("p7", 64, 6),
                                                ("C1", 24, 6), ("C4s", 28, 3), ("C4", 24, 1), ("C4", 28, 1), ("C5", 24, 1),
-                                               ("C5", 28, 1), ("d40", 28, 6), ("h15", 24, 6), ("p7", 28, 6), ("t3", 24, 8)])
+                                               ("C5", 28, 1), ("d40", 28, 6), ("h15", 24, 6), ("p7", 28, 6), ("t3", 24, 8),
+                                               ("d140", 0, 2), ("d140", 24, 2), ("d140", 128, 2), ("d140", 32, 2)])
 def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     nw = 10 if shape not in ("C4", "C5") else 7
     cfg, H, R, k = make_walkers(shape, nw, seed=31)
