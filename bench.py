@@ -436,6 +436,7 @@ def run_b200(args):
             "dense_regime": dense,
         }
         print(json.dumps(line), flush=True)
+    ns.close()
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()

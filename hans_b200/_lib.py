@@ -62,7 +62,8 @@ EXPORTS = [
     "hans_mc_run_batch_ws", "hans_mc_run_launches", "hans_gen_proposals",
     "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
-    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_order_params", "hans_diag_counters",
+    "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ns_peer_bytes", "hans_peer_alloc",
+    "hans_peer_open", "hans_peer_close", "hans_peer_free", "hans_ns_exchange_peer", "hans_order_params", "hans_diag_counters",
     "hans_ffma_peak",
 ]
 
@@ -124,6 +125,12 @@ def _load():
     L.hans_ns_resolve.argtypes = [C.POINTER(NsArgs), vp]
     L.hans_order_params.argtypes = [cp, vp, vp, i32, vp, vp, vp]
     L.hans_diag_counters.argtypes = [vp, i32]
+    L.hans_ns_peer_bytes.argtypes = [i32, i32]; L.hans_ns_peer_bytes.restype = C.c_uint64
+    L.hans_peer_alloc.argtypes = [u64, C.POINTER(vp), C.c_char_p]
+    L.hans_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.hans_peer_close.argtypes = [vp]
+    L.hans_peer_free.argtypes = [vp]
+    L.hans_ns_exchange_peer.argtypes = [C.POINTER(NsArgs), C.POINTER(vp), vp]
     L.hans_ffma_peak.argtypes = [i32, C.POINTER(f64), vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -126,7 +126,7 @@ __device__ void block_argmax(const double *vol, int n, double &best, int &bi)
 }
 
 // local MAXLOC (mpihans.py:211-212) and staging of the clone source (mpihans.py:226-229)
-__global__ void ns_pack_kernel(const hans_ns_args a)
+__device__ __forceinline__ void ns_pack_body(const hans_ns_args &a)
 {
     double best; int bi;
     block_argmax(a.d_vol, a.nlocal, best, bi);
@@ -143,10 +143,11 @@ __global__ void ns_pack_kernel(const hans_ns_args a)
         for (int i = threadIdx.x; i < n3; i += blockDim.x) a.d_rec[12 + i] = r[i];
     }
 }
+__global__ void ns_pack_kernel(const hans_ns_args a) { ns_pack_body(a); }
 
 // global MAXLOC (mpihans.py:215), ceiling, log, trajectory staging, clone (mpihans.py:232-237),
 // active walkers (mpihans.py:236-239)
-__global__ void ns_resolve_kernel(const hans_ns_args a)
+__device__ __forceinline__ void ns_resolve_body(const hans_ns_args &a, const double *gathered)
 {
     __shared__ double s_vmax;
     __shared__ int s_rank, s_idx;
@@ -155,8 +156,8 @@ __global__ void ns_resolve_kernel(const hans_ns_args a)
     if (threadIdx.x == 0) {
         double best = -1.7976931348623157e308; int br = 0, bi = 0;
         for (int r = 0; r < a.world; ++r) {
-            const double v = a.d_gathered[(size_t)r * rec];
-            if (v > best) { best = v; br = r; bi = (int)a.d_gathered[(size_t)r * rec + 1]; }
+            const double v = gathered[(size_t)r * rec];
+            if (v > best) { best = v; br = r; bi = (int)gathered[(size_t)r * rec + 1]; }
         }
         s_vmax = best; s_rank = br; s_idx = bi;
         *a.d_limit = best;
@@ -180,7 +181,7 @@ __global__ void ns_resolve_kernel(const hans_ns_args a)
             for (int i = threadIdx.x; i < n3; i += blockDim.x) t[12 + i] = dr[i];
             __syncthreads();
         }
-        const double *sr = a.d_gathered + (size_t)src_rank * rec;
+        const double *sr = gathered + (size_t)src_rank * rec;
         if (threadIdx.x == 0) a.d_vol[midx] = sr[2];
         if (threadIdx.x < 9) a.d_H[(size_t)midx * 9 + threadIdx.x] = sr[3 + threadIdx.x];
         for (int i = threadIdx.x; i < n3; i += blockDim.x) dr[i] = sr[12 + i];
@@ -194,6 +195,53 @@ __global__ void ns_resolve_kernel(const hans_ns_args a)
     }
     __syncthreads();
     if (threadIdx.x == 0) *a.d_iter = it + 1;
+}
+__global__ void ns_resolve_kernel(const hans_ns_args a) { ns_resolve_body(a, a.d_gathered); }
+
+// ---------------------------------------------------------------------------------------------
+// The exchange of an iteration over NVLink peer memory instead of a collective library: ONE kernel
+// per rank does pack -> push -> wait -> resolve.  Every rank owns a buffer that all ranks of the node
+// have mapped (CUDA IPC): flags[2][world] (u64, padded to 128 bytes) + records[2][world][12+3N]
+// (float64); the leading index is the parity of the iteration.  A rank stores the live part of its
+// record into slot [parity][rank] of EVERY rank's buffer (plain stores through the peer mapping,
+// fence.sys), then raises flag [parity][rank] there to iteration + 1 (st.release.sys); it then spins
+// (ld.acquire.sys) until the `world` flags of that parity in its OWN buffer have reached
+// iteration + 1 and resolves from its own copy.  Two parities suffice: a rank can only write
+// iteration i + 2 after it has seen every rank's flag of iteration i + 1, which each rank raises
+// after it has finished reading iteration i (stream order).  Flags only grow, so nothing is reset.
+// ---------------------------------------------------------------------------------------------
+struct PeerTable { unsigned long long *base[HANS_PEER_MAX]; };
+__host__ __device__ inline size_t peer_header_words(int world) { return (size_t)((2 * world + 15) / 16) * 16; }
+
+__global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_args a, const PeerTable pt)
+{
+    const int rec = 12 + 3 * a.N, world = a.world;
+    const long long it = *a.d_iter;
+    const int par = (int)(it & 1);
+    const size_t hdr = peer_header_words(world);
+    ns_pack_body(a); // -> a.d_rec
+    __syncthreads();
+    const unsigned long long K = (unsigned long long)a.nlocal * (unsigned long long)world;
+    const int src_rank = (int)((ns_draw(a.seed, it, 0u, 0u) % K) / (unsigned long long)a.nlocal);
+    const int len = src_rank == a.rank ? rec : 2; // only the owner of the clone source ships a configuration
+    for (int p = 0; p < world; ++p) {
+        double *dst = reinterpret_cast<double *>(pt.base[p] + hdr) + ((size_t)par * world + a.rank) * rec;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = a.d_rec[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    const unsigned long long want = (unsigned long long)it + 1ull;
+    if ((int)threadIdx.x < world) {
+        unsigned long long *f = pt.base[threadIdx.x] + (size_t)par * world + a.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(want) : "memory");
+        const unsigned long long *g = pt.base[a.rank] + (size_t)par * world + threadIdx.x;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(g) : "memory");
+        } while (v < want);
+    }
+    __syncthreads();
+    ns_resolve_body(a, reinterpret_cast<const double *>(pt.base[a.rank] + hdr) + (size_t)par * world * rec);
 }
 
 // Order parameters of n configurations (nematic.py:83-137 nematic P2; nematic.py:30-55 translational), one warp
@@ -797,6 +845,57 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream)
     int rc = check_ns(a);
     if (rc) return rc;
     ns_resolve_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a);
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+uint64_t hans_ns_peer_bytes(int N, int world)
+{
+    if (N < 1 || world < 1) return 0;
+    return 8ull * (peer_header_words(world) + 2ull * (uint64_t)world * (uint64_t)(12 + 3 * N));
+}
+
+int hans_peer_alloc(uint64_t bytes, void **d_ptr, unsigned char *handle64)
+{
+    if (!d_ptr || !handle64 || bytes == 0) return fail(HANS_EINVAL, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemset(p, 0, bytes));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return HANS_OK;
+}
+
+int hans_peer_open(const unsigned char *handle64, void **d_ptr)
+{
+    if (!d_ptr || !handle64) return fail(HANS_EINVAL, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return HANS_OK;
+}
+
+int hans_peer_close(void *d_ptr) { if (d_ptr) CK(cudaIpcCloseMemHandle(d_ptr)); return HANS_OK; }
+int hans_peer_free(void *d_ptr) { if (d_ptr) CK(cudaFree(d_ptr)); return HANS_OK; }
+
+int hans_ns_exchange_peer(const hans_ns_args *a, void *const *peer_bufs, void *stream)
+{
+    int rc = check_ns(a);
+    if (rc) return rc;
+    if (!peer_bufs) return fail(HANS_EINVAL, "peer_bufs is NULL");
+    if (a->world > HANS_PEER_MAX) return fail(HANS_ELIMIT, "more ranks than HANS_PEER_MAX");
+    PeerTable pt;
+    memset(&pt, 0, sizeof pt);
+    for (int r = 0; r < a->world; ++r) {
+        if (!peer_bufs[r]) return fail(HANS_EINVAL, "NULL peer buffer");
+        pt.base[r] = (unsigned long long *)peer_bufs[r];
+    }
+    ns_exchange_peer_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a, pt);
     CK(cudaGetLastError());
     return HANS_OK;
 }

@@ -304,6 +304,7 @@ def main(SimParams, comm: "_Dist | None" = None):
     write_restart(i - 1)  # mpihans.py:294-298
     sys.stdout.flush()
     comm.barrier()
+    ns.close()  # (peer-memory exchange buffers, if HANS_NS_PEER=1)
 
     # ---- analysis hook (mpihans.py:308-329) ---------------------------------------------------------
     if SimParams["analyse"] and rank == 0:

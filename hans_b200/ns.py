@@ -13,10 +13,15 @@ Per iteration the host enqueues, with no synchronisation:
     hans_mc_run_batch  walklength sweeps for the active walkers            (mpihans.py:241-245)
 The clone source is a shared Philox draw keyed by the iteration number, so no broadcast of the
 choice is needed; the ceiling, iteration counter and active list stay in device memory.
+
+With HANS_NS_PEER=1 (one node, world > 1) the first three become ONE kernel, hans_ns_exchange_peer:
+records are stored straight into CUDA-IPC-mapped buffers of the other ranks over NVLink and a flag
+per rank and iteration replaces the collective (include/hans_b200.h).  Opt-in: not measured yet.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -110,6 +115,45 @@ class NestedSampler:
         a.d_limit, a.d_log, a.d_ids = self.d_limit.data_ptr(), self.d_log.data_ptr(), self.d_ids.data_ptr()
         a.d_traj, a.d_traj_iter = self.d_traj.data_ptr(), self.d_traj_iter.data_ptr()
         self.args = a
+        self._peer = None
+        if self.world > 1 and os.environ.get("HANS_NS_PEER", "0") == "1":
+            self._setup_peer()
+
+    def _setup_peer(self) -> None:
+        """Map one exchange buffer per rank into every rank of the node (CUDA IPC); include/hans_b200.h."""
+        import torch.distributed as dist
+        if self.world > 16:
+            raise ValueError("HANS_NS_PEER supports up to 16 ranks on one node")
+        nbytes = int(lib.hans_ns_peer_bytes(self.pool.N, self.world))
+        mine = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(lib.hans_peer_alloc(nbytes, C.byref(mine), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        table = (C.c_void_p * self.world)()
+        opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                table[r] = mine.value
+            else:
+                p = C.c_void_p()
+                check(lib.hans_peer_open(handles[r], C.byref(p)))
+                table[r] = p.value
+                opened.append(p.value)
+        dist.barrier(group=self.group)
+        self._peer = dict(mine=mine.value, opened=opened, table=table)
+
+    def close(self) -> None:
+        """Release the peer-memory exchange buffers (no-op on the NCCL path)."""
+        if self._peer is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.pool.device)
+            dist.barrier(group=self.group)
+            for p in self._peer["opened"]:
+                check(lib.hans_peer_close(p))
+            dist.barrier(group=self.group)
+            check(lib.hans_peer_free(self._peer["mine"]))
+            self._peer = None
 
     # ---- the iteration --------------------------------------------------------------------------
     def step_with_events(self, ev0, ev1) -> None:
@@ -119,12 +163,16 @@ class NestedSampler:
     def step(self, ev0=None, ev1=None) -> None:
         """Enqueue one NS iteration (mpihans.py:210-245).  No host synchronisation."""
         st = _stream()
-        check(lib.hans_ns_pack(C.byref(self.args), st))
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.gathered, self.rec, group=self.group)
-        check(lib.hans_ns_resolve(C.byref(self.args), st))
-        self.pool.launches += 2
+        if self._peer is not None:
+            check(lib.hans_ns_exchange_peer(C.byref(self.args), self._peer["table"], st))
+            self.pool.launches += 1
+        else:
+            check(lib.hans_ns_pack(C.byref(self.args), st))
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.gathered, self.rec, group=self.group)
+            check(lib.hans_ns_resolve(C.byref(self.args), st))
+            self.pool.launches += 2
         ids = None if self.nw == 1 else self.d_ids  # nw == 1: every resident walker walks
         if ev0 is not None:
             ev0.record()

@@ -262,6 +262,23 @@ int hans_ns_pack(const hans_ns_args *a, void *stream);
  * walker list (mpihans.py:236-239), iteration counter += 1 */
 int hans_ns_resolve(const hans_ns_args *a, void *stream);
 
+/* ---- the same exchange over NVLink peer memory (one node, CUDA IPC) -----------------------------------
+ * hans_ns_exchange_peer = hans_ns_pack + all-gather + hans_ns_resolve in ONE kernel per rank: every rank
+ * stores its record straight into a buffer of every other rank and raises a flag there; each rank
+ * waits for the world flags in its own buffer and resolves from its own copy (no collective library,
+ * no kernel boundary; protocol in hans_kernels.cu).  Set-up, once: every rank calls hans_peer_alloc
+ * (hans_ns_peer_bytes(N, world) bytes, zeroed) and publishes the 64-byte handle to the other ranks of
+ * the node; each rank opens the others' handles (hans_peer_open) and passes the world base pointers --
+ * its own at index rank -- as the HOST array peer_bufs.  a->d_gathered is not used (but must be non-NULL).
+ * Opt-in in the host layer (HANS_NS_PEER=1); the NCCL all_gather path is the default. */
+#define HANS_PEER_MAX 16
+uint64_t hans_ns_peer_bytes(int N, int world);
+int hans_peer_alloc(uint64_t bytes, void **d_ptr, unsigned char *handle64);
+int hans_peer_open(const unsigned char *handle64, void **d_ptr);
+int hans_peer_close(void *d_ptr);
+int hans_peer_free(void *d_ptr);
+int hans_ns_exchange_peer(const hans_ns_args *a, void *const *peer_bufs, void *stream);
+
 /* ---- order parameters (the reference's offline nematic.py) ---------------------------
  * For n configurations: d_p2[k] = nematic order parameter P2, the largest eigenvalue of
  * Q = mean over chains of (3 u u^T - I)/2 with u the unit minimum-image end-to-end vector

@@ -121,3 +121,13 @@ def test_workspace_plan_launch_count():
     assert L.hans_mc_run_launches(1024, 2840, 1, 1000 * per_move) == 2 * 3    # 992 moves fit: generate, walk, three times
     assert L.hans_mc_run_launches(1024, 2840, 0, 0) == 1                       # no workspace: generation inside the walk kernel
     assert L.hans_mc_run_launches(8, 87, 1, 8 * 64 * 40) == 2 * 3              # 32 of 87 moves fit
+
+
+def test_peer_exchange_buffer_size():
+    """hans_ns_peer_bytes: flags[2][world] u64 padded to 128 bytes + records[2][world][12 + 3N] float64."""
+    from hans_b200 import _lib
+    L = _lib.lib
+    assert L.hans_ns_peer_bytes(96, 8) == 8 * (16 + 2 * 8 * (12 + 288))
+    assert L.hans_ns_peer_bytes(768, 2) == 8 * (16 + 2 * 2 * (12 + 2304))
+    assert L.hans_ns_peer_bytes(64, 16) == 8 * (32 + 2 * 16 * (12 + 192))
+    assert L.hans_ns_peer_bytes(0, 2) == 0
