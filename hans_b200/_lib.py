@@ -63,7 +63,7 @@ EXPORTS = [
     "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
     "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ns_peer_bytes", "hans_peer_alloc",
-    "hans_peer_open", "hans_peer_close", "hans_peer_free", "hans_ns_exchange_peer", "hans_order_params", "hans_diag_counters",
+    "hans_peer_open", "hans_peer_close", "hans_peer_free", "hans_ns_exchange_peer", "hans_ns_peer_timeout", "hans_order_params", "hans_diag_counters",
     "hans_ffma_peak",
 ]
 
@@ -131,6 +131,7 @@ def _load():
     L.hans_peer_close.argtypes = [vp]
     L.hans_peer_free.argtypes = [vp]
     L.hans_ns_exchange_peer.argtypes = [C.POINTER(NsArgs), C.POINTER(vp), vp]
+    L.hans_ns_peer_timeout.argtypes = [f64]
     L.hans_ffma_peak.argtypes = [i32, C.POINTER(f64), vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -213,7 +213,7 @@ __global__ void ns_resolve_kernel(const hans_ns_args a) { ns_resolve_body(a, a.d
 struct PeerTable { unsigned long long *base[HANS_PEER_MAX]; };
 __host__ __device__ inline size_t peer_header_words(int world) { return (size_t)((2 * world + 15) / 16) * 16; }
 
-__global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_args a, const PeerTable pt)
+__global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_args a, const PeerTable pt, long long spin_limit)
 {
     const int rec = 12 + 3 * a.N, world = a.world;
     const long long it = *a.d_iter;
@@ -236,8 +236,11 @@ __global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_arg
         asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(want) : "memory");
         const unsigned long long *g = pt.base[a.rank] + (size_t)par * world + threadIdx.x;
         unsigned long long v;
+        const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(g) : "memory");
+            // (default: wait for ever, like a collective; hans_ns_peer_timeout bounds it for tests)
+            if (spin_limit > 0 && v < want && clock64() - t0 > spin_limit) { atomicAdd(&g_diag[2], 1ull); break; }
         } while (v < want);
     }
     __syncthreads();
@@ -849,6 +852,13 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream)
     return HANS_OK;
 }
 
+static long long g_peer_spin_limit = 0; // SM clock cycles; 0 = no limit
+int hans_ns_peer_timeout(double seconds)
+{
+    g_peer_spin_limit = seconds > 0.0 ? (long long)(seconds * 1.9e9) : 0;
+    return HANS_OK;
+}
+
 uint64_t hans_ns_peer_bytes(int N, int world)
 {
     if (N < 1 || world < 1) return 0;
@@ -895,7 +905,7 @@ int hans_ns_exchange_peer(const hans_ns_args *a, void *const *peer_bufs, void *s
         if (!peer_bufs[r]) return fail(HANS_EINVAL, "NULL peer buffer");
         pt.base[r] = (unsigned long long *)peer_bufs[r];
     }
-    ns_exchange_peer_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a, pt);
+    ns_exchange_peer_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(*a, pt, g_peer_spin_limit);
     CK(cudaGetLastError());
     return HANS_OK;
 }

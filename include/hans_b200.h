@@ -278,6 +278,9 @@ int hans_peer_open(const unsigned char *handle64, void **d_ptr);
 int hans_peer_close(void *d_ptr);
 int hans_peer_free(void *d_ptr);
 int hans_ns_exchange_peer(const hans_ns_args *a, void *const *peer_bufs, void *stream);
+/* bound the wait for the other ranks' flags (seconds of SM clock; 0 = wait for ever, the default, like a
+ * collective).  A wait that expires is counted in hans_diag_counters out4[2] and the iteration's result is void. */
+int hans_ns_peer_timeout(double seconds);
 
 /* ---- order parameters (the reference's offline nematic.py) ---------------------------
  * For n configurations: d_p2[k] = nematic order parameter P2, the largest eigenvalue of
@@ -289,7 +292,8 @@ int hans_order_params(const hans_cfg *cfg, const double *d_H, const double *d_R,
                       double *d_trans, void *stream);
 
 /* Diagnostics (synchronises): out4[0] = trial chains re-tested in float64 because a pair fell into
- * the float32 filter's band, out4[1] = float64 all-pairs passes of box moves; reset != 0 zeroes them. */
+ * the float32 filter's band, out4[1] = float64 all-pairs passes of box moves, out4[2] = expired waits of
+ * hans_ns_exchange_peer; reset != 0 zeroes them. */
 int hans_diag_counters(uint64_t *out4, int reset);
 
 /* FP32 FFMA issue-rate probe used as the roofline denominator in bench.py: runs `iters`
