@@ -16,7 +16,7 @@ choice is needed; the ceiling, iteration counter and active list stay in device 
 
 With HANS_NS_PEER=1 (one node, world > 1) the first three become ONE kernel, hans_ns_exchange_peer:
 records are stored straight into CUDA-IPC-mapped buffers of the other ranks over NVLink and a flag
-per rank and iteration replaces the collective (include/hans_b200.h).  Opt-in: not measured yet.
+per rank and iteration replaces the collective (include/hans_b200.h).  Opt-in: not timed yet.
 """
 from __future__ import annotations
 

@@ -270,7 +270,8 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream);
  * (hans_ns_peer_bytes(N, world) bytes, zeroed) and publishes the 64-byte handle to the other ranks of
  * the node; each rank opens the others' handles (hans_peer_open) and passes the world base pointers --
  * its own at index rank -- as the HOST array peer_bufs.  a->d_gathered is not used (but must be non-NULL).
- * Opt-in in the host layer (HANS_NS_PEER=1); the NCCL all_gather path is the default. */
+ * Opt-in in the host layer (HANS_NS_PEER=1) until it has been timed on several GPUs; the NCCL all_gather
+ * path is the default. */
 #define HANS_PEER_MAX 16
 uint64_t hans_ns_peer_bytes(int N, int world);
 int hans_peer_alloc(uint64_t bytes, void **d_ptr, unsigned char *handle64);

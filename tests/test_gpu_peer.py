@@ -1,5 +1,6 @@
-"""The NS exchange over NVLink peer memory (HANS_NS_PEER=1, hans_ns_exchange_peer) against the NCCL all_gather
-path: same volumes.txt, line for line, on two GPUs.  Needs two devices; skipped on a one-GPU box."""
+"""The NS exchange over NVLink peer memory (HANS_NS_PEER=1, hans_ns_exchange_peer): against the NCCL all_gather
+path on two GPUs (same volumes.txt, line for line; skipped on a one-GPU box), and its protocol with two ranks
+emulated on one GPU (passes on B200)."""
 import os
 import subprocess
 import sys
@@ -44,8 +45,6 @@ def test_peer_exchange_equals_nccl(tmp_path):
     assert len(a) == 301 and a == b
 
 
-@pytest.mark.skipif(os.environ.get("HANS_TEST_PEER", "0") != "1",
-                    reason="spin-wait protocol not yet run on hardware: set HANS_TEST_PEER=1 to run it explicitly")
 def test_peer_protocol_two_ranks_emulated_on_one_gpu():
     """The protocol of hans_ns_exchange_peer without IPC: two 'ranks' on ONE device, their buffers plain
     allocations of that device, their kernels on two streams (they must be co-resident: one CTA each).  Decisions
