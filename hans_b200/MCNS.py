@@ -4,15 +4,17 @@ Same function names, argument meaning and return values as /root/reference/NesSa
 code written against ``from NesSa import MCNS as NS`` runs with
 ``from hans_b200 import MCNS as NS``.  `NS.alk` is the hs_alkane stand-in (hans_b200/alk.py).
 
-Two ways to do a walk:
-  * MC_run                -- the drop-in: ONE fused kernel launch (hans_mc_run_batch) replaces the
-                             Python move loop of MCNS.py:304-383 for the box.
-  * MC_run_python_loop    -- the reference's own per-move control flow (MCNS.py:304-383) driven
-                             through the alk entry points, kept for semantic cross-checks.
+`MC_run` is the drop-in: ONE fused kernel launch (hans_mc_run_batch) replaces the Python move loop
+of MCNS.py:304-383 for the box.  The helpers around it keep the reference's names and signatures
+but are written for this engine: whole-box array operations on the host mirror of the walker state
+and single calls into the C ABI where the reference loops over chains and beads in Python.  The
+reference's own move loop is NOT restated here -- tests/test_reference_live_cpu.py executes the
+unmodified /root/reference/NesSa/MCNS.py against the CPU checker and records its call sequence,
+which tests/test_gpu_reference_golden.py replays on `alk`.
 """
 from __future__ import annotations
 
-import ctypes as C
+import math
 import sys
 
 import numpy as np
@@ -25,159 +27,55 @@ move_types = ['box', 'translate', 'rotate', 'dihedral', 'shear', 'stretch']  # M
 ivol = 0; itrans = 1; irot = 2; idih = 3; ishear = 4; istr = 5                 # MCNS.py:27
 
 
+def _box(ibox):
+    """Host mirror (cell, beads) of box `ibox` (1-based), as writable arrays."""
+    w = alk._w(ibox)
+    alk._pool()
+    return alk._S.H[w], alk._S.R[w]
+
+
 def mk_ase_config(ibox, Nbeads, Nchains, scaling=3.75):
-    """MCNS.py:30-53: the box as an Atoms object (ase is replaced by hans_b200.atoms.Atoms)."""
-    model_positions = np.empty([Nchains * Nbeads, 3])
-    cell_vectors = alk.box_get_cell(int(ibox))
-    for ichain in range(0, Nchains):
-        model_positions[Nbeads * ichain:Nbeads * ichain + Nbeads] = alk.alkane_get_chain(int(ichain + 1), int(ibox))
-    confstring = "C" + str(Nbeads * Nchains)
-    return Atoms(confstring, positions=model_positions * scaling, pbc=True, cell=cell_vectors * scaling)
+    """MCNS.py:30-53: box `ibox` as an Atoms object (ase is replaced by hans_b200.atoms.Atoms); one slice
+    of the host mirror instead of a loop over chains."""
+    H, R = _box(ibox)
+    n = int(Nbeads) * int(Nchains)
+    return Atoms("C%d" % n, positions=R[:n] * scaling, pbc=True, cell=H * scaling)
 
 
 def min_aspect_ratio(ibox):
-    """MCNS.py:97-118."""
-    vol = alk.box_compute_volume(int(ibox))
-    cell = alk.box_get_cell(int(ibox)).copy()
-    best = sys.float_info.max
-    for i in range(3):
-        vi = cell[i, :]
-        vnorm_hat = np.cross(cell[(i + 1) % 3, :], cell[(i + 2) % 3, :])
-        vnorm_hat = vnorm_hat / (np.sqrt(np.dot(vnorm_hat, vnorm_hat)))
-        best = min(best, abs(np.dot(vnorm_hat, vi)))
-    return best / np.cbrt(vol)
+    """MCNS.py:97-118, evaluated by the device metrics kernel (hans_cell_metrics)."""
+    return alk.box_min_aspect_ratio(ibox)
 
 
 def min_angle(ibox):
-    """MCNS.py:120-133 (radians)."""
-    cell = alk.box_get_cell(int(ibox)).copy()
-    best = sys.float_info.max
-    for i in range(3):
-        vc1 = cell[(i + 1) % 3, :]
-        vc2 = cell[(i + 2) % 3, :]
-        dot_prod = np.dot(vc1, vc2) / np.sqrt((np.dot(vc1, vc1)) * (np.dot(vc2, vc2)))
-        if dot_prod < 0:
-            dot_prod *= -1
-        best = min(best, np.arccos(dot_prod))
-    return best
+    """MCNS.py:120-133 (radians): arccos of the largest |cos| between two cell vectors (hans_cell_metrics)."""
+    return math.acos(min(1.0, float(alk._metrics(alk._w(ibox))[2])))
+
+
+def _shape_proposal(kind, step_size):
+    """Draws of box_shear_step (MCNS.py:148,174-175) / box_stretch_step (MCNS.py:222-227) as one proposal
+    record: the vector indices from alk's uniform stream, the amplitudes from numpy's global normal stream."""
+    prop = np.zeros(1, dtype=_lib.PROPOSAL_DTYPE)
+    prop["type"] = kind
+    i = min(int(alk.random_uniform_random() * 3), 2)
+    if kind == _lib.SHEAR:
+        prop["idx0"] = i
+        prop["p"][0, :2] = np.random.normal(scale=step_size, size=2)
+    else:
+        j = min(int(alk.random_uniform_random() * 3), 2)
+        prop["idx0"], prop["idx1"] = i, (j + 1) % 3 if j == i else j
+        prop["p"][0, 0] = np.random.normal(scale=step_size)
+    return prop
 
 
 def box_shear_step(ibox, step_size, aspect_ratio_limit=0.8, angle_limit=60):
-    """MCNS.py:135-207: returns (boltz, delta_H); the box is left sheared, the caller reverts."""
-    rnd_vec_ind = int(np.floor(alk.random_uniform_random() * 3))
-    other_vec_ind = list(range(3))
-    other_vec_ind.remove(rnd_vec_ind)
-    orig_cell_copy = alk.box_get_cell(int(ibox)).copy()
-    v1 = orig_cell_copy[other_vec_ind[0], :].copy()
-    v2 = orig_cell_copy[other_vec_ind[1], :].copy()
-    v1 /= np.sqrt(np.dot(v1, v1))
-    v2 -= v1 * np.dot(v1, v2)
-    v2 /= np.sqrt(np.dot(v2, v2))
-    if np.isnan(np.sum(v1)) or np.isnan(np.sum(v2)):
-        raise FloatingPointError("box_shear_step: degenerate cell")  # the reference prints and sys.exit()s
-    rv1 = np.random.normal(scale=step_size)
-    rv2 = np.random.normal(scale=step_size)
-    new_cell = orig_cell_copy.copy()
-    new_cell[rnd_vec_ind, :] += rv1 * v1 + rv2 * v2
-    delta_H = new_cell - orig_cell_copy
-    alk.alkane_change_box(int(ibox), delta_H)
-    angle_limit_rad = angle_limit * np.pi / 180
-    if alk.box_min_aspect_ratio(ibox) < aspect_ratio_limit:
-        boltz = 0
-    elif min_angle(ibox) < angle_limit_rad:
-        boltz = 0
-    elif alk.alkane_check_chain_overlap(int(ibox)):
-        boltz = 0
-    else:
-        boltz = 1
-    return boltz, delta_H
+    """MCNS.py:135-207 on the device: returns (boltz, delta_H); the box is left sheared, the caller reverts."""
+    return alk._shape_step(ibox, _shape_proposal(_lib.SHEAR, step_size), aspect_ratio_limit, angle_limit)
 
 
 def box_stretch_step(ibox, step_size, aspect_ratio_limit=0.8, angle_limit=60):
-    """MCNS.py:209-252."""
-    cell = alk.box_get_cell(int(ibox))
-    new_cell = cell.copy()
-    rnd_v1_ind = int(np.floor(alk.random_uniform_random() * 3))
-    rnd_v2_ind = int(np.floor(alk.random_uniform_random() * 3))
-    if rnd_v1_ind == rnd_v2_ind:
-        rnd_v2_ind = (rnd_v2_ind + 1) % 3
-    rv = np.random.normal(scale=step_size)
-    new_cell[rnd_v1_ind] *= np.exp(rv)
-    new_cell[rnd_v2_ind] *= np.exp(-rv)
-    delta_H = new_cell - cell
-    alk.alkane_change_box(int(ibox), delta_H)
-    angle_limit_rad = angle_limit * np.pi / 180
-    if alk.box_min_aspect_ratio(ibox) < aspect_ratio_limit:
-        boltz = 0
-    elif min_angle(ibox) < angle_limit_rad:
-        boltz = 0
-    elif alk.alkane_check_chain_overlap(int(ibox)):
-        boltz = 0
-    else:
-        boltz = 1
-    return boltz, delta_H
-
-
-def _moves_per_sweep(nbeads, nchains):
-    return _lib.moves_per_sweep(nbeads, nchains)  # MCNS.py:296-301
-
-
-def MC_run_python_loop(ns_data, sweeps, move_ratio, ibox, volume_limit=sys.float_info.max, return_ase=False,
-                       dshear=1.0, dstretch=1.0, min_ang=60, min_ar=0.8, pressure=0):
-    """The reference's move loop, MCNS.py:276-392, statement for statement, on the alk stand-in."""
-    moves_accepted = np.zeros(6)
-    moves_attempted = np.zeros(6)
-    nbeads = ns_data["nbeads"]
-    nchains = ns_data["nchains"]
-    move_prob = np.cumsum(move_ratio) / np.sum(move_ratio)
-    moves_per_sweep = _moves_per_sweep(nbeads, nchains)
-    for _ in range(int(sweeps)):
-        for _ in range(moves_per_sweep):
-            ichain = int(np.floor(alk.random_uniform_random() * nchains))
-            current_chain = alk.alkane_get_chain(int(ichain + 1), int(ibox))
-            backup_chain = current_chain.copy()
-            xi = np.random.random()
-            if xi < move_prob[ivol]:
-                itype = ivol
-                boltz = alk.alkane_box_resize(pressure, int(ibox), 0)
-            elif xi < move_prob[itrans]:
-                itype = itrans
-                boltz = alk.alkane_translate_chain(int(ichain + 1), int(ibox))
-            elif xi < move_prob[irot]:
-                itype = irot
-                boltz, quat = alk.alkane_rotate_chain(int(ichain + 1), int(ibox), 0)
-            elif xi < move_prob[idih]:
-                itype = idih
-                boltz, bead1, angle = alk.alkane_bond_rotate(int(ichain + 1), int(ibox), 1)
-            elif xi < move_prob[ishear]:
-                itype = ishear
-                boltz, delta_H = box_shear_step(ibox, dshear, min_ar, min_ang)
-            else:
-                itype = istr
-                boltz, delta_H = box_stretch_step(ibox, dstretch, min_ar, min_ang)
-            moves_attempted[itype] += 1
-            if itype == ivol:
-                new_volume = alk.box_compute_volume(int(ibox))
-                if (np.random.random() < boltz) and (new_volume - volume_limit) < sys.float_info.epsilon:
-                    moves_accepted[itype] += 1
-                else:
-                    alk.alkane_box_resize(pressure, int(ibox), 1)
-            elif itype == ishear or itype == istr:
-                if boltz:
-                    moves_accepted[itype] += 1
-                else:
-                    alk.alkane_change_box(int(ibox), -1.0 * delta_H)
-            else:
-                if np.random.random() < boltz:
-                    moves_accepted[itype] += 1
-                else:
-                    for ibead in range(nbeads):
-                        current_chain[ibead] = backup_chain[ibead]
-    moves_attempted = np.where(moves_attempted == 0, 1, moves_attempted)
-    rate = moves_accepted / moves_attempted
-    if return_ase:
-        return mk_ase_config(ibox, nbeads, nchains, scaling=1)
-    return alk.box_compute_volume(int(ibox)), rate
+    """MCNS.py:209-252 on the device: returns (boltz, delta_H)."""
+    return alk._shape_step(ibox, _shape_proposal(_lib.STRETCH, step_size), aspect_ratio_limit, angle_limit)
 
 
 def _run_fused(boxes, sweeps, move_ratio, volume_limit, dshear, dstretch, min_ang, min_ar, pressure):
@@ -226,16 +124,10 @@ def MC_run_batch(ns_data, sweeps, move_ratio, iboxes, volume_limit=sys.float_inf
 
 
 def clone_walker(ibox_source, ibox_clone):
-    """MCNS.py:510-524."""
-    nbeads = alk.alkane_get_nbeads()
-    nchains = alk.alkane_get_nchains()
-    cell = alk.box_get_cell(ibox_source)
-    alk.box_set_cell(ibox_clone, cell)
-    for ichain in range(1, nchains + 1):
-        original_chain = alk.alkane_get_chain(ichain, ibox_source)
-        clone_chain = alk.alkane_get_chain(ichain, ibox_clone)
-        for ibead in range(nbeads):
-            clone_chain[ibead][:] = original_chain[ibead][:]
+    """MCNS.py:510-524: cell and beads of one box over another (two array copies on the host mirror)."""
+    (Hs, Rs), (Hd, Rd) = _box(ibox_source), _box(ibox_clone)
+    Hd[...] = Hs
+    Rd[...] = Rs
 
 
 def perturb_initial_configs(ns_data, move_ratio, walk_length=20):
@@ -247,89 +139,63 @@ def perturb_initial_configs(ns_data, move_ratio, walk_length=20):
 
 
 def import_ase_to_ibox(atoms, ibox, ns_data, scaling=1.0):
-    """MCNS.py:550-580."""
-    try:
-        nbeads = ns_data.parameters.nbeads
-        nchains = ns_data.parameters.nchains
-    except AttributeError:
-        nbeads = ns_data["nbeads"]
-        nchains = ns_data["nchains"]
-    cell_vectors = np.array(atoms.cell, dtype=np.float64)
-    if cell_vectors.size == 3:
-        cell_vectors = cell_vectors * np.eye(3)
-    alk.box_set_cell(int(ibox), cell_vectors * scaling)
-    positions = atoms.get_positions()
-    for ichain in range(1, nchains + 1):
-        chain = alk.alkane_get_chain(ichain, int(ibox))
-        for ibead in range(nbeads):
-            chain[ibead][:] = positions[(ichain - 1) * nbeads + ibead][:] * scaling
+    """MCNS.py:550-580: write an Atoms object (cubic `cell` of 3 numbers or a full 3x3) into box `ibox`."""
+    H, R = _box(ibox)
+    cell = np.asarray(atoms.cell, dtype=np.float64)
+    H[...] = (np.diag(cell) if cell.size == 3 else cell.reshape(3, 3)) * scaling
+    pos = np.asarray(atoms.get_positions(), dtype=np.float64)
+    R[...] = pos[:R.shape[0]] * scaling
+
+
+# hs_alkane's set-up protocol (MCNS.py:595-606): (entry point, key of `args` or literal value), in call order
+_SETUP = (("box_set_num_boxes", "nwalkers"), ("box_initialise", None), ("box_set_pbc", 1),
+          ("alkane_set_nchains", "nchains"), ("alkane_set_nbeads", "nbeads"), ("alkane_initialise", None),
+          ("box_set_isotropic", 1), ("box_set_bypass_link_cells", 1), ("box_set_use_verlet_list", 0),
+          ("alkane_set_bondlength", "bondlength"), ("alkane_set_bondangle", "bondangle"))
 
 
 def initialise_sim_cells(args, quiet):
-    """MCNS.py:582-606."""
+    """MCNS.py:582-606: configure the engine and allocate `nwalkers` boxes on the device."""
     alk.box_set_quiet(quiet)
-    alk.box_set_num_boxes(args["nwalkers"])
-    alk.box_initialise()
-    alk.box_set_pbc(1)
-    alk.alkane_set_nchains(int(args["nchains"]))
-    alk.alkane_set_nbeads(int(args["nbeads"]))
-    alk.alkane_initialise()
-    alk.box_set_isotropic(1)
-    alk.box_set_bypass_link_cells(1)
-    alk.box_set_use_verlet_list(0)
-    alk.alkane_set_bondlength(float(args["bondlength"]))
-    alk.alkane_set_bondangle(float(args["bondangle"]))
+    for name, what in _SETUP:
+        fn = getattr(alk, name)
+        if what is None:
+            fn()
+        else:
+            v = args[what] if isinstance(what, str) else what
+            fn(float(v) if name.startswith("alkane_set_bond") else int(v))
 
 
 def default_move_ratio(ns_data):
-    """MCNS.py:610-626 (a missing `from_restart` counts as 0 -- the README input lacks it)."""
-    if "move_ratio" in ns_data:
-        mr = ns_data["move_ratio"]
-        if isinstance(mr, str):
-            move_ratio = [float(i) for i in mr.split(',')]
-        else:
-            move_ratio = list(np.asarray(mr, dtype=np.float64))
-        if len(move_ratio) != 6:
+    """MCNS.py:610-626: the six move weights (volume, translate, rotate, dihedral, shear, stretch), from the input's
+    `move_ratio` (string "a,b,c,d,e,f" or array) or the per-degree-of-freedom default.  A missing `from_restart`
+    counts as 0 -- the README input lacks it."""
+    given = ns_data.get("move_ratio") if hasattr(ns_data, "get") else None
+    if given is not None:
+        mr = np.array([float(x) for x in given.split(",")] if isinstance(given, str) else given, dtype=np.float64).ravel()
+        if mr.size != 6:
             raise Exception("Move ratio array should be of length 6.")
-        return np.array(move_ratio, dtype=np.float64)
-    move_ratio = np.zeros(6)
-    move_ratio[ivol] = 1
-    move_ratio[itrans] = 3.0 * ns_data["nchains"]
-    move_ratio[irot] = (2.0 * ns_data["nchains"]) if ns_data["nbeads"] >= 2 else 0
-    move_ratio[idih] = 1.0 * max(((ns_data["nbeads"] - 3.0) * (ns_data["nchains"]), 0))
-    move_ratio[ishear] = 3
-    move_ratio[istr] = 3
-    return np.array(move_ratio)
+        return mr
+    nc, nb = float(ns_data["nchains"]), int(ns_data["nbeads"])
+    return np.array([1.0, 3.0 * nc, 2.0 * nc * (nb >= 2), nc * max(nb - 3.0, 0.0), 3.0, 3.0])
 
 
 def create_initial_configs(args, max_vol_per_atom=15):
-    """MCNS.py:628-632."""
-    cell_matrix = 0.999 * np.eye(3) * np.cbrt(args["nbeads"] * args["nchains"] * max_vol_per_atom)
-    for ibox in range(1, args["nwalkers"] + 1):
-        alk.box_set_cell(int(ibox), cell_matrix)
+    """MCNS.py:628-632: cubic cells of side 0.999 cbrt(max_vol_per_atom N) for every box, then growth."""
+    alk._pool()
+    side = 0.999 * np.cbrt(args["nbeads"] * args["nchains"] * max_vol_per_atom)
+    alk._S.H[: args["nwalkers"]] = side * np.eye(3)
     populate_boxes(args)
 
 
 def populate_boxes(args):
-    """MCNS.py:634-644, all boxes grown by one kernel launch (hans_grow)."""
+    """MCNS.py:634-644: all chains of all boxes grown by ONE kernel launch (hans_grow) instead of the reference's
+    retry loop over alkane_grow_chain calls."""
     pool = alk._pool()
     alk._upload_all()
     pool.grow()
     alk._download_all()
     alk.alkane_set_nchains(args["nchains"])
-
-
-def populate_boxes_python_loop(args):
-    """MCNS.py:634-644 statement for statement (one alkane_grow_chain call per attempt)."""
-    ncopy = args["nchains"]
-    for ibox in range(1, args["nwalkers"] + 1):
-        for ichain in range(1, ncopy + 1):
-            rb_factor = 0
-            alk.alkane_set_nchains(ichain)
-            while rb_factor == 0:
-                rb_factor, ifail = alk.alkane_grow_chain(ichain, int(ibox), 1)
-                if ifail != 0:
-                    rb_factor = 0
 
 
 class SingleComm:

@@ -61,7 +61,7 @@ EXPORTS = [
     "hans_moves_per_sweep", "hans_default_threads_per_walker", "hans_default_window", "hans_default_team", "hans_mc_run_batch",
     "hans_mc_run_batch_ws", "hans_mc_run_launches", "hans_gen_proposals",
     "hans_replay",
-    "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_grow", "hans_grow_chain",
+    "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_shape_delta", "hans_grow", "hans_grow_chain",
     "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ns_peer_bytes", "hans_peer_alloc",
     "hans_peer_open", "hans_peer_close", "hans_peer_free", "hans_ns_exchange_peer", "hans_ns_peer_timeout", "hans_order_params", "hans_diag_counters",
     "hans_ffma_peak",
@@ -117,6 +117,7 @@ def _load():
     L.hans_check_overlap.argtypes = [cp, vp, vp, vp, i32, i32, vp, i32, vp]
     L.hans_cell_metrics.argtypes = [vp, i32, vp, vp, vp, vp]
     L.hans_change_box.argtypes = [cp, vp, vp, vp, i32, vp, vp]
+    L.hans_shape_delta.argtypes = [vp, vp, i32, vp, vp, vp]
     L.hans_grow.argtypes = [cp, vp, vp, i32, u64, u32, i32, vp, vp]
     L.hans_grow_chain.argtypes = [cp, vp, vp, i32, i32, u64, u32, u32, vp, vp]
     L.hans_argmax.argtypes = [vp, i32, vp, vp]

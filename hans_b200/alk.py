@@ -53,6 +53,7 @@ class _State:
         self.rng = np.random.default_rng(0)
         self.grow_attempt = 0
         self.seed = 0
+        self.script = None  # explicit proposals for the move entry points (replay of a recorded call sequence)
 
 
 _S = _State()
@@ -243,6 +244,26 @@ def random_set_random_seed(seed) -> None:
 
 
 # ---- moves (MCNS.py:186,238,318-333,357,368,642) ------------------------------------------------------
+def set_proposal_script(records) -> None:
+    """Parity hook (not part of hs_alkane): the next calls of alkane_translate_chain / alkane_rotate_chain /
+    alkane_bond_rotate / alkane_box_resize(.., 0) take their random amplitudes from `records` (hans_proposal
+    records, in call order) instead of the generator -- hs_alkane draws them inside the Fortran, so a recorded
+    call sequence of the reference can only be replayed with the amplitudes made explicit.  None = off."""
+    from collections import deque
+    _S.script = None if records is None else deque(np.asarray(r, dtype=PROPOSAL_DTYPE).reshape(1).copy() for r in records)
+
+
+def _scripted(kind: int, c=None):
+    if _S.script is None:
+        return None
+    if not _S.script:
+        raise _lib.HansError("proposal script exhausted")
+    prop = _S.script.popleft()
+    if int(prop["type"][0]) != kind or (c is not None and int(prop["ichain"][0]) != c):
+        raise _lib.HansError("proposal script does not match the call (type %d / chain %s)" % (kind, c))
+    return prop
+
+
 def _propose(w: int, prop: np.ndarray, pressure: float = 0.0):
     """Run ONE explicit proposal on box w in hs_alkane entry-point semantics (trial state is left
     in place, the caller reverts): host box -> device, hans_replay(MODE_PROPOSE), device -> host."""
@@ -257,9 +278,11 @@ def _propose(w: int, prop: np.ndarray, pressure: float = 0.0):
 def alkane_translate_chain(ichain, ibox) -> float:
     """Rigid shift of one chain by dr_max*(2U-1) per component; returns 0.0 on overlap else 1.0."""
     w, c = _w(ibox), _c(ichain)
-    prop = np.zeros(1, dtype=PROPOSAL_DTYPE)
-    prop["type"], prop["ichain"] = _lib.TRANS, c
-    prop["p"][0, :3] = _S.steps["dr_max"] * (2.0 * _S.rng.random(3) - 1.0)
+    prop = _scripted(_lib.TRANS, c)
+    if prop is None:
+        prop = np.zeros(1, dtype=PROPOSAL_DTYPE)
+        prop["type"], prop["ichain"] = _lib.TRANS, c
+        prop["p"][0, :3] = _S.steps["dr_max"] * (2.0 * _S.rng.random(3) - 1.0)
     return float(_propose(w, prop)["boltz"])
 
 
@@ -268,6 +291,9 @@ def alkane_rotate_chain(ichain, ibox, bond=0):
     first bond vector instead of a random axis.  Returns (boltz, quaternion[4])."""
     w, c = _w(ibox), _c(ichain)
     nb = _S.nbeads
+    prop = _scripted(_lib.ROT, c)
+    if prop is not None:
+        return float(_propose(w, prop)["boltz"]), prop["p"][0].copy()
     if int(bond) and nb >= 2:
         x = _S.R[w][c * nb:(c + 1) * nb]
         axis = x[1] - x[0]
@@ -289,6 +315,9 @@ def alkane_bond_rotate(ichain, ibox, allow_flip=1):
     (1-based), angle)."""
     w, c = _w(ibox), _c(ichain)
     nb = _S.nbeads
+    prop = _scripted(_lib.DIH, c)
+    if prop is not None:
+        return float(_propose(w, prop)["boltz"]), int(prop["idx0"][0]) + 1, float(prop["p"][0, 0])
     prop = np.zeros(1, dtype=PROPOSAL_DTYPE)
     prop["type"], prop["ichain"] = _lib.DIH, c
     if nb < 4:
@@ -314,9 +343,11 @@ def alkane_box_resize(pressure, ibox, reset=0) -> float:
             _S.R[w][...] = R
         return 1.0
     _S.saved[w] = (_S.H[w].copy(), _S.R[w].copy())
-    prop = np.zeros(1, dtype=PROPOSAL_DTYPE)
-    prop["type"] = _lib.VOL
-    prop["p"][0, 0] = _S.steps["dv_max"] * (2.0 * _S.rng.random() - 1.0)
+    prop = _scripted(_lib.VOL)
+    if prop is None:
+        prop = np.zeros(1, dtype=PROPOSAL_DTYPE)
+        prop["type"] = _lib.VOL
+        prop["p"][0, 0] = _S.steps["dv_max"] * (2.0 * _S.rng.random() - 1.0)
     prop["u_acc"] = 0.0
     return float(_propose(w, prop, pressure=float(pressure))["boltz"])
 
@@ -328,6 +359,26 @@ def alkane_change_box(ibox, delta_H) -> None:
     _up(w)
     p.change_box([w], np.asarray(delta_H, dtype=np.float64).reshape(1, 3, 3))
     _down(w)
+
+
+def _shape_step(ibox, prop: np.ndarray, min_ar: float, min_ang_deg: float):
+    """box_shear_step / box_stretch_step (MCNS.py:135-252) for one explicit proposal: the box is left at the trial
+    cell (the caller reverts, MCNS.py:366-368).  Returns (boltz 0/1, delta_H (3,3)) -- two launches:
+    hans_shape_delta for the cell change the reference's Python builds, hans_replay(MODE_PROPOSE) for the move."""
+    w = _w(ibox)
+    p = _pool()
+    _up(w)
+    f64 = dict(dtype=torch.float64, device=p.device)
+    d_ids = torch.tensor([w], dtype=torch.int32, device=p.device)
+    d_prop = torch.as_tensor(prop.view(np.uint8).reshape(-1)).to(p.device)
+    d_dH = torch.empty(9, **f64)
+    _lib.check(_lib.lib.hans_shape_delta(p.H.data_ptr(), d_ids.data_ptr(), 1, d_prop.data_ptr(), d_dH.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    p.cfg.min_ar = float(min_ar)
+    p.cfg.cos_min_ang = math.cos(float(min_ang_deg) * _PI / 180.0)
+    dec = p.replay([w], prop.reshape(1, 1), mode=MODE_PROPOSE)[0, 0]
+    _down(w)
+    return int(dec["boltz"] != 0.0), d_dH.cpu().numpy().reshape(3, 3)
 
 
 def alkane_box_scale(ibox, sa, sb, sc) -> None:

@@ -27,6 +27,24 @@ __global__ void metrics_kernel(const double *gH, int n, double *vol, double *mar
     if (mcos) mcos[i] = max_abs_cos(H);
 }
 
+// delta_H of n shear / stretch proposals on the cells of walkers ids[k] (box_shear_step MCNS.py:148-184,
+// box_stretch_step MCNS.py:220-234); other proposal types give zero
+__global__ void shape_delta_kernel(const double *gH, const int32_t *ids, int n, const hans_proposal *props, double *dH)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int wi = ids ? ids[k] : k;
+    double H[9], d[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { H[q] = gH[(size_t)wi * 9 + q]; d[q] = 0.0; }
+    const hans_proposal p = props[k];
+    const bool shear = p.type == HANS_SHEAR && (unsigned)p.idx0 < 3u;
+    const bool stretch = p.type == HANS_STRETCH && (unsigned)p.idx0 < 3u && (unsigned)p.idx1 < 3u && p.idx0 != p.idx1;
+    if (shear || stretch) shape_delta(H, p.type, p.idx0, p.idx1, p.p[0], p.p[1], d);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) dH[(size_t)k * 9 + q] = d[q];
+}
+
 // local MAXLOC (mpihans.py:211-212): ties -> lowest index
 __global__ void argmax_kernel(const double *vol, int n, double *out2)
 {
@@ -753,6 +771,16 @@ int hans_change_box(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t
         if (rc) return rc;
         change_box_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, d_dH);
     });
+    CK(cudaGetLastError());
+    return HANS_OK;
+}
+
+int hans_shape_delta(const double *d_H, const int32_t *d_ids, int n, const hans_proposal *d_props, double *d_dH, void *stream)
+{
+    if (!d_H || !d_props || !d_dH) return fail(HANS_EINVAL, "NULL device pointer");
+    if (n < 0) return fail(HANS_EINVAL, "negative count");
+    if (n == 0) return HANS_OK;
+    shape_delta_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_H, d_ids, n, d_props, d_dH);
     CK(cudaGetLastError());
     return HANS_OK;
 }

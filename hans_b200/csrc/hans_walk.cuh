@@ -854,6 +854,39 @@ template <int T> __device__ __forceinline__ void commit_trial(const WCtx &w)
     gsync<T>();
 }
 
+// delta_H of a shear / stretch proposal exactly as the reference's Python builds it: box_shear_step
+// (MCNS.py:148-184: Gram-Schmidt of the two other cell vectors with np.dot, delta_H[k] = (H[k] + rv1 v1 + rv2 v2) - H[k])
+// and box_stretch_step (MCNS.py:220-234: delta_H[i] = H[i] e^rv - H[i], delta_H[j] = H[j] e^-rv - H[j]).  dH must be zeroed.
+__device__ __forceinline__ void shape_delta(const double *H, int type, int idx0, int idx1, double p0, double p1, double *dH)
+{
+    if (type == HANS_SHEAR) {
+        const int k = idx0;
+        const int o0 = (k == 0) ? 1 : 0;
+        const int o1 = (k == 2) ? 1 : 2;
+        double v1[3] = {H[3 * o0], H[3 * o0 + 1], H[3 * o0 + 2]};
+        double v2[3] = {H[3 * o1], H[3 * o1 + 1], H[3 * o1 + 2]};
+        const double n1 = sqrt(dot3_blas(v1, v1)); // np.dot, MCNS.py:161
+        v1[0] /= n1; v1[1] /= n1; v1[2] /= n1;
+        const double pr = dot3_blas(v1, v2);
+        v2[0] -= v1[0] * pr; v2[1] -= v1[1] * pr; v2[2] -= v1[2] * pr;
+        const double n2 = sqrt(dot3_blas(v2, v2));
+        v2[0] /= n2; v2[1] /= n2; v2[2] /= n2;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double nw = H[3 * k + a] + (p0 * v1[a] + p1 * v2[a]);
+            dH[3 * k + a] = nw - H[3 * k + a];
+        }
+    } else {
+        const int i = idx0, j = idx1;
+        const double e1 = hd_exp(p0), e2 = hd_exp(-p0);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dH[3 * i + a] = H[3 * i + a] * e1 - H[3 * i + a];
+            dH[3 * j + a] = H[3 * j + a] * e2 - H[3 * j + a];
+        }
+    }
+}
+
 struct DecP { int accepted, reason; double boltz; unsigned pairs; };
 
 // alk.alkane_box_resize(pressure, ibox, 0) + acceptance (MCNS.py:318,349-357), and
@@ -897,32 +930,7 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
             if (!(p->u_acc < boltz_f)) { out.reason = HANS_REJ_BOLTZ; return out; }
         }
     } else {
-        if (p->type == HANS_SHEAR) {
-            const int k = p->idx0;
-            const int o0 = (k == 0) ? 1 : 0;
-            const int o1 = (k == 2) ? 1 : 2;
-            double v1[3] = {H[3 * o0], H[3 * o0 + 1], H[3 * o0 + 2]};
-            double v2[3] = {H[3 * o1], H[3 * o1 + 1], H[3 * o1 + 2]};
-            const double n1 = sqrt(dot3(v1, v1));
-            v1[0] /= n1; v1[1] /= n1; v1[2] /= n1;
-            const double pr = dot3(v1, v2);
-            v2[0] -= v1[0] * pr; v2[1] -= v1[1] * pr; v2[2] -= v1[2] * pr;
-            const double n2 = sqrt(dot3(v2, v2));
-            v2[0] /= n2; v2[1] /= n2; v2[2] /= n2;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double nw = H[3 * k + a] + (p->p[0] * v1[a] + p->p[1] * v2[a]);
-                dH[3 * k + a] = nw - H[3 * k + a];
-            }
-        } else {
-            const int i = p->idx0, j = p->idx1;
-            const double e1 = hd_exp(p->p[0]), e2 = hd_exp(-p->p[0]);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                dH[3 * i + a] = H[3 * i + a] * e1 - H[3 * i + a];
-                dH[3 * j + a] = H[3 * j + a] * e2 - H[3 * j + a];
-            }
-        }
+        shape_delta(H, p->type, p->idx0, p->idx1, p->p[0], p->p[1], dH);
 #pragma unroll
         for (int k = 0; k < 9; ++k) Hn[k] = H[k] + dH[k];
     }

@@ -191,6 +191,13 @@ int hans_cell_metrics(const double *d_H, int n, double *d_vol, double *d_min_ar,
 int hans_change_box(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t *d_ids, int n,
                     const double *d_dH, void *stream);
 
+/* The cell change a shear / stretch proposal makes, as the reference's Python builds it: delta_H of
+ * box_shear_step (MCNS.py:148-184) and box_stretch_step (MCNS.py:220-234), the value those functions
+ * return and MC_run reverts with (MCNS.py:366-368).  d_props[n] (one per walker d_ids[k]), d_dH[n][9];
+ * proposals of other types give zero.  Does not touch the walkers. */
+int hans_shape_delta(const double *d_H, const int32_t *d_ids, int n, const hans_proposal *d_props,
+                     double *d_dH, void *stream);
+
 /* ---- initial configurations -------------------------------------------------------------------
  * create_initial_configs + populate_boxes (MCNS.py:628-644): cells must already be set in d_H;
  * grows all chains of n walkers by random insertion (retry until no overlap, at most

@@ -104,6 +104,15 @@ static double dot3(const double *a, const double *b)
     return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
 }
 
+/* np.dot of two 3-vectors as numpy evaluates it in this image (OpenBLAS ddot on an FMA machine):
+ * fma(a2,b2, fma(a1,b1, a0*b0)) -- established by tests/test_reference_live_cpu.py against the
+ * reference executed here.  Used where the reference's Python calls np.dot on the shear path
+ * (MCNS.py:161-163), so that delta_H is bit-identical to the reference's. */
+static double dot3_blas(const double *a, const double *b)
+{
+    return hd_fma(a[2], b[2], hd_fma(a[1], b[1], a[0] * b[0]));
+}
+
 static void cross3(const double *a, const double *b, double *o)
 {
     o[0] = a[1] * b[2] - a[2] * b[1];
@@ -565,11 +574,11 @@ static void move_shape(const ho_cfg *c, double *H, double *R, const ho_proposal 
         int o1 = (k == 2) ? 1 : 2;
         double v1[3] = { H[3 * o0], H[3 * o0 + 1], H[3 * o0 + 2] };
         double v2[3] = { H[3 * o1], H[3 * o1 + 1], H[3 * o1 + 2] };
-        double n1 = sqrt(dot3(v1, v1));                 /* MCNS.py:161 */
+        double n1 = sqrt(dot3_blas(v1, v1));               /* MCNS.py:161 */
         v1[0] /= n1; v1[1] /= n1; v1[2] /= n1;
-        double pr = dot3(v1, v2);                       /* MCNS.py:162 */
+        double pr = dot3_blas(v1, v2);                /* MCNS.py:162 */
         v2[0] -= v1[0] * pr; v2[1] -= v1[1] * pr; v2[2] -= v1[2] * pr;
-        double n2 = sqrt(dot3(v2, v2));                 /* MCNS.py:163 */
+        double n2 = sqrt(dot3_blas(v2, v2));               /* MCNS.py:163 */
         v2[0] /= n2; v2[1] /= n2; v2[2] /= n2;
         for (int a = 0; a < 3; ++a) {                   /* MCNS.py:182-184 */
             double nw = H[3 * k + a] + (p->p[0] * v1[a] + p->p[1] * v2[a]);

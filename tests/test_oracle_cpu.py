@@ -332,3 +332,28 @@ def test_order_parameter_known_answers():
     frac = rng.uniform(0, 1, (4000, 3))
     assert op.trans_order_param([cell], [frac @ cell], 1, 4000)[0] < 0.06
     assert op.nematic_order_param([cell], [frac[:27] @ cell], 1, 27)[0] == 0.0
+
+
+# ---- the oracle against vectors made by executing the unmodified reference (tests/golden/make_ref_live_golden.py) ----
+@pytest.mark.parametrize("shape", ["tiny1", "tiny", "p7", "t3", "C1", "C2", "h15", "dimer", "C4s"])
+def test_oracle_reproduces_reference_golden(oracle, shape):
+    """tests/golden/ref_live_replay.npz holds what /root/reference/NesSa/MCNS.py:MC_run made of explicit proposals
+    (run in the build container; the file travels, the reference does not).  Decisions must be identical; the state
+    bit-identical to the run with the deterministic exp, and within 1e-13 of the run with numpy's exp."""
+    z = np.load(os.path.join(HERE, "golden", "ref_live_replay.npz"))
+    tr = json.load(open(os.path.join(HERE, "golden", "ref_live_trace.json")))
+    nchains, nbeads, sweeps = (int(x) for x in z[shape + ".shape"])
+    cfg = oracle.make_cfg(nchains, nbeads, z[shape + ".move_ratio"], min_ar=tr["min_ar"], min_ang=tr["min_ang"], **tr["step_kw"])
+    props = z[shape + ".props"].view(oracle.PROPOSAL_DTYPE)
+    assert len(props) == sweeps * oracle.moves_per_sweep(nbeads, nchains)
+    H, R = z[shape + ".H0"].copy(), z[shape + ".R0"].copy()
+    dec = oracle.replay(cfg, H, R, props, volume_limit=float(z[shape + ".limit"][0]))
+    att = np.bincount(props["type"], minlength=6).astype(float)
+    acc = np.bincount(props["type"], weights=dec["accepted"], minlength=6)
+    rates = acc / np.where(att == 0, 1, att)
+    assert np.array_equal(rates, z[shape + ".rates_np"]) and np.array_equal(rates, z[shape + ".rates_det"])
+    assert np.array_equal(H.view(np.uint64), z[shape + ".H_det"].view(np.uint64))
+    assert np.array_equal(R.view(np.uint64), z[shape + ".R_det"].view(np.uint64))
+    assert oracle.volume(H) == float(z[shape + ".vol_det"][0])
+    scale = max(np.abs(R).max(), np.abs(H).max())
+    assert np.abs(R - z[shape + ".R_np"]).max() <= 1e-13 * scale and np.abs(H - z[shape + ".H_np"]).max() <= 1e-13 * scale
