@@ -86,21 +86,30 @@ def restart_paths(filename: str):
     return [filename, _npz_name(filename)]
 
 
+def _datasets(entry) -> dict:
+    """(coordinates, unitcell[, philox_ctr]) -> the datasets of one walker group.  `philox_ctr` (one float64: the
+    number of proposals the walker has consumed, exact below 2^53) is an addition of this implementation so that a
+    resumed run continues the random streams instead of replaying them; the reference's reader ignores it."""
+    d = {"coordinates": np.asarray(entry[0], dtype=np.float64).reshape(-1, 3),
+         "unitcell": np.asarray(entry[1], dtype=np.float64).reshape(3, 3)}
+    if len(entry) > 2 and entry[2] is not None:
+        d["philox_ctr"] = np.asarray([float(entry[2])], dtype=np.float64)
+    return d
+
+
 def save_restart(filename: str, attrs: dict, walkers: dict) -> str:
-    """walkers: {groupname: (coordinates (N,3), unitcell (3,3))}.  Returns the path written."""
+    """walkers: {groupname: (coordinates (N,3), unitcell (3,3)[, philox counter])}.  Returns the path written."""
     if HAVE_H5PY:  # pragma: no cover
         with h5py.File(filename, "w") as f:
             for k, v in attrs.items():
                 f.attrs.create(k, v)
-            for g, (coords, cell) in walkers.items():
+            for g, entry in walkers.items():
                 grp = f.create_group(g)
-                grp.create_dataset("coordinates", data=np.asarray(coords, dtype=np.float64))
-                grp.create_dataset("unitcell", data=np.asarray(cell, dtype=np.float64))
+                for name, arr in _datasets(entry).items():
+                    grp.create_dataset(name, data=arr)
         return filename
     tmp = filename + ".tmp"
-    h5min.write(tmp, attrs, {g: {"coordinates": np.asarray(coords, dtype=np.float64).reshape(-1, 3),
-                                  "unitcell": np.asarray(cell, dtype=np.float64).reshape(3, 3)}
-                             for g, (coords, cell) in walkers.items()})
+    h5min.write(tmp, attrs, {g: _datasets(entry) for g, entry in walkers.items()})
     os.replace(tmp, filename)
     return filename
 
@@ -113,11 +122,17 @@ def open_restart(filename: str):
             for k in f.attrs:
                 attrs[k] = f.attrs[k]
             for g in f:
-                walkers[g] = (f[g]["coordinates"][:], f[g]["unitcell"][:])
+                ctr = float(f[g]["philox_ctr"][0]) if "philox_ctr" in f[g] else None
+                walkers[g] = (f[g]["coordinates"][:], f[g]["unitcell"][:], ctr)
         return attrs, walkers
     if os.path.exists(filename) and h5min.is_hdf5(filename):
-        attrs, groups = h5min.read(filename)
-        return attrs, {g: (d["coordinates"], d["unitcell"]) for g, d in groups.items()}
+        try:
+            attrs, groups = h5min.read(filename)
+        except Exception as e:
+            raise ValueError(f"{filename} is an HDF5 file this package's minimal reader cannot parse (written by libhdf5 "
+                             f"with features outside the restart schema's subset?) and h5py is not installed: {e}") from e
+        return attrs, {g: (d["coordinates"], d["unitcell"], float(d["philox_ctr"][0]) if "philox_ctr" in d else None)
+                       for g, d in groups.items()}
     path = _npz_name(filename)  # the container written before h5min existed
     if not os.path.exists(path):
         raise FileNotFoundError(f"no restart file {filename} (or {path})")
@@ -129,7 +144,7 @@ def open_restart(filename: str):
                 attrs[k[5:]] = v.item() if v.shape == () else v
             else:
                 g, ds = k.rsplit("/", 1)
-                walkers.setdefault(g, [None, None])[0 if ds == "coordinates" else 1] = z[k]
+                walkers.setdefault(g, [None, None, None])[0 if ds == "coordinates" else 1] = z[k]
     return attrs, {g: tuple(v) for g, v in walkers.items()}
 
 
@@ -148,13 +163,27 @@ def restart_attrs(args: dict, i: int, steps: dict) -> dict:
     return attrs
 
 
-def write_to_restart(args, rank_states, filename="restart.hdf5", i=0, steps=None) -> str:
-    """NSio.py:69-111.  rank_states[r] = (H (nw,3,3), R (nw,N,3)) for every rank r, already gathered
-    on the writing rank (the reference ssend/recvs lists of Atoms, NSio.py:96-110)."""
+def walker_group(vrank: int, iwalker: int) -> str:
+    """NSio.py:87: group of walker `iwalker` (0-based) of MPI rank `vrank`; 1-based, :04d."""
+    return f"walker_{vrank}_{iwalker + 1:04d}"
+
+
+def write_to_restart(args, rank_states, filename="restart.hdf5", i=0, steps=None, nwalkers=None) -> str:
+    """NSio.py:69-111.  rank_states[g] = (H (nlocal,3,3), R (nlocal,N,3)[, ctr (nlocal,)]) for every GPU g, already
+    gathered on the writing rank (the reference ssend/recvs lists of Atoms, NSio.py:96-110).  Groups are named per
+    VIRTUAL rank -- `nwalkers` walkers each, the reference's per-MPI-rank count -- so the file is what `size` MPI ranks
+    of the reference would have written (mpihans.py:171-179 reads walker_{rank}_{1..nwalkers}) and does not depend on
+    how the virtual ranks were spread over GPUs."""
     walkers = {}
-    for r, (H, R) in enumerate(rank_states):
+    g0 = 0
+    for st in rank_states:
+        H, R = st[0], st[1]
+        ctr = st[2] if len(st) > 2 else None
+        nw = int(nwalkers) if nwalkers else H.shape[0]
         for iw in range(H.shape[0]):
-            walkers[f"walker_{r}_{iw + 1:04d}"] = (R[iw], H[iw])  # NSio.py:87, 1-based, :04d
+            g = g0 + iw
+            walkers[walker_group(g // nw, g % nw)] = (R[iw], H[iw], None if ctr is None else int(ctr[iw]))
+        g0 += H.shape[0]
     return save_restart(filename, restart_attrs(args, i, steps or {}), walkers)
 
 

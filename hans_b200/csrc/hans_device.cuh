@@ -118,7 +118,7 @@ __device__ __forceinline__ double dot3(const double *a, const double *b)
 }
 
 // np.dot of two 3-vectors as numpy (OpenBLAS ddot, FMA hardware) evaluates it: the shear path of the
-// reference (MCNS.py:161-163) is Python, and the oracle is pinned to it executed live (tests/test_reference_live_cpu.py)
+// reference (MCNS.py:161-163) is Python, and tests/test_reference_live_cpu.py compares delta_H with the reference executed live
 __device__ __forceinline__ double dot3_blas(const double *a, const double *b)
 {
     return hd_fma(a[2], b[2], hd_fma(a[1], b[1], a[0] * b[0]));

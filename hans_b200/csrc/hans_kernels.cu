@@ -339,17 +339,25 @@ __global__ void order_kernel(const hans_cfg cfg, const double *gH, const double 
     }
 }
 
-// FP32 FFMA issue-rate probe (roofline denominator)
-__global__ void ffma_kernel(int iters, float *sink)
+// FP32 FFMA issue-rate probe (roofline denominator): 16 independent accumulators, 64 FFMAs per loop trip, so the
+// loop overhead (compare + branch + counter) is < 5 % of the issue slots
+#define HANS_FFMA_PER_TRIP 64
+__global__ void __launch_bounds__(256) ffma_kernel(int iters, float *sink)
 {
-    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
-    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = threadIdx.x * 1e-3f + (float)k;
     const float m = 0.999f, c = 1e-3f;
+#pragma unroll 1
     for (int i = 0; i < iters; ++i) {
-        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
-        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+#pragma unroll
+        for (int u = 0; u < HANS_FFMA_PER_TRIP / 16; ++u)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = __fmaf_rn(a[k], m, c);
     }
-    const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
     if (s == 123456.789f) sink[0] = s;
 }
 
@@ -975,13 +983,17 @@ int hans_ffma_peak(int iters, double *tflops, void *stream)
     CK(cudaEventCreate(&e1));
     const int blocks = sm_count() * 8, threads = 256;
     ffma_kernel<<<blocks, threads, 0, st>>>(iters, sink); // warm-up
-    CK(cudaEventRecord(e0, st));
-    ffma_kernel<<<blocks, threads, 0, st>>>(iters, sink);
-    CK(cudaEventRecord(e1, st));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    float best = 0.f;
+    for (int rep = 0; rep < 3; ++rep) { // best of three: the probe is a peak, not an average
+        CK(cudaEventRecord(e0, st));
+        ffma_kernel<<<blocks, threads, 0, st>>>(iters, sink);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep == 0 || ms < best) best = ms;
+    }
+    *tflops = 2.0 * (double)HANS_FFMA_PER_TRIP * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);

@@ -105,17 +105,19 @@ class _Dist:
             self.dist.barrier(group=self.group)
 
     def gather_states(self, pool):
-        """Every rank's (H, R) on every rank (restart writer, NSio.py:96-110)."""
+        """Every rank's (H, R, Philox counters) on every rank (restart writer, NSio.py:96-110)."""
         import torch
         if self.world == 1:
             H, R = pool.get_state()
-            return [(H, R)]
+            return [(H, R, pool.ctr.cpu().numpy())]
         gH = torch.empty((self.world,) + tuple(pool.H.shape), dtype=torch.float64, device=pool.device)
         gR = torch.empty((self.world,) + tuple(pool.R.shape), dtype=torch.float64, device=pool.device)
+        gC = torch.empty((self.world,) + tuple(pool.ctr.shape), dtype=torch.int64, device=pool.device)
         self.dist.all_gather_into_tensor(gH, pool.H.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(gR, pool.R.contiguous(), group=self.group)
-        gH, gR = gH.cpu().numpy(), gR.cpu().numpy()
-        return [(gH[r], gR[r]) for r in range(self.world)]
+        self.dist.all_gather_into_tensor(gC, pool.ctr.contiguous(), group=self.group)
+        gH, gR, gC = gH.cpu().numpy(), gR.cpu().numpy(), gC.cpu().numpy()
+        return [(gH[r], gR[r], gC[r]) for r in range(self.world)]
 
     def close(self):
         if self.world > 1:
@@ -234,10 +236,19 @@ def main(SimParams, comm: "_Dist | None" = None):
     else:
         H = np.zeros((nlocal, 3, 3))
         R = np.zeros((nlocal, pool.N, 3))
-        for iw in range(nlocal):  # each rank reads its own groups, mpihans.py:171-179
-            coords, cell = restart_walkers[f"walker_{rank}_{iw + 1:04d}"]
-            H[iw], R[iw] = cell, coords
+        ctr = np.zeros(nlocal, dtype=np.int64)
+        for iw in range(nlocal):  # each (virtual) rank reads its own groups, mpihans.py:171-179
+            g = rank * nlocal + iw
+            name = NSio.walker_group(g // nw, g % nw)
+            if name not in restart_walkers:
+                raise KeyError(f"{name} is not in the restart file: it holds {len(restart_walkers)} walkers, this run expects "
+                               f"{nw} walkers x {size} ranks (nwalkers x GPUs x ranks_per_gpu must match, mpihans.py:171-179)")
+            entry = restart_walkers[name]
+            H[iw], R[iw] = entry[1], entry[0]
+            if len(entry) > 2 and entry[2] is not None:
+                ctr[iw] = int(entry[2])  # continue the walker's proposal stream (the reference saves no RNG state)
         pool.set_state(H, R)
+        pool.ctr.copy_(torch.as_tensor(ctr))
     torch.cuda.synchronize(dev)
 
     K = nw * size
@@ -245,6 +256,9 @@ def main(SimParams, comm: "_Dist | None" = None):
     dof = compute_dof(SimParams, move_ratio)
     restart_interval = int(SimParams.get("restart_interval", RESTART_INTERVAL))
     traj_interval = int(SimParams.get("traj_interval", TRAJ_INTERVAL))
+    if restart_interval < 1:
+        restart_interval = 1 << 62  # 0 / negative: no periodic restart files (one is still written at the end)
+    traj_interval = max(traj_interval, 0)  # 0: no trajectory
 
     f = None
     if rank == 0:
@@ -265,7 +279,7 @@ def main(SimParams, comm: "_Dist | None" = None):
         if rank == 0:
             _rotate_restart("restart.hdf5")
             to_store = {k: v for k, v in SimParams.items()}
-            NSio.write_to_restart(to_store, states, filename="restart.hdf5", i=i, steps=ns.steps())
+            NSio.write_to_restart(to_store, states, filename="restart.hdf5", i=i, steps=ns.steps(), nwalkers=nw)
             print("wrote to restart")
         sys.stdout.flush()
 

@@ -105,7 +105,6 @@ class NestedSampler:
         self.walk_counters = False
         self.att = self.acc = None
         self._scratch: Optional[WalkerPool] = None
-        self._rng = np.random.default_rng([self.seed, self.rank, 0x5ca1ab1e])
         a = NsArgs()
         a.N, a.nlocal, a.rank, a.world = pool.N, pool.nwalkers, self.rank, self.world
         a.nw_per_vrank, a.traj_interval, a.traj_slots, a.log_cap = self.nw, self.traj_interval, self.traj_slots, self.log_cap
@@ -244,9 +243,14 @@ class NestedSampler:
                                        threads_per_walker=pool.tpw, **pool._cfg_kw)
         sc = self._scratch
         C.memmove(C.byref(sc.cfg), C.byref(pool.cfg), C.sizeof(_lib.Cfg))
+        # Everything random here is a pure function of (seed, rank, iteration): a run resumed from a restart file
+        # adapts exactly like the uninterrupted run (the reference saves no RNG state at all).  The trial walks draw
+        # from their own Philox streams (walker ids above 0x40000000), positioned by the iteration.
+        rng = np.random.default_rng([self.seed, self.rank, self.iteration, 0x5ca1ab1e])
+        sc.ctr.fill_(self.iteration << 24)
         # one random walker of A distinct virtual ranks (MCNS.py:676)
-        vr = self._rng.choice(self.nvranks, size=A, replace=False)
-        picks = vr * self.nw + self._rng.integers(0, self.nw, size=A)
+        vr = rng.choice(self.nvranks, size=A, replace=False)
+        picks = vr * self.nw + rng.integers(0, self.nw, size=A)
         idx = torch.as_tensor(np.tile(picks, 6), device=pool.device)
         sc.H.copy_(pool.H[idx])
         sc.R.copy_(pool.R[idx])

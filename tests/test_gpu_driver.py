@@ -142,8 +142,12 @@ restart_interval = 200
     attrs, walkers = NSio.open_restart("run1/restart.hdf5")
     assert attrs["prev_iters"] == 230 and len(walkers) == 24 and attrs["dv_max"] > 0
     assert NSio.restart_exists("run1/restart_backup.hdf5")
-    assert walkers["walker_0_0001"][0].shape == (32, 3) and walkers["walker_0_0024"][1].shape == (3, 3)
-    # resume for 40 more iterations
+    # groups are named per VIRTUAL rank, nwalkers each: what 4 MPI ranks x 6 walkers of the reference would write
+    # (NSio.py:87, mpihans.py:171-179), independent of ranks_per_gpu
+    assert sorted(walkers) == [f"walker_{r}_{i:04d}" for r in range(4) for i in range(1, 7)]
+    assert walkers["walker_0_0001"][0].shape == (32, 3) and walkers["walker_3_0006"][1].shape == (3, 3)
+    assert all(w[2] is not None and w[2] > 0 for w in walkers.values())   # Philox counters travel with the walkers
+    # resume: `iterations` is restored from the file (as in the reference), so 230 more run
     P2 = NSio.parse_hans_text("from_restart = 1\ndirectory = run1\n")
     mpihans.main(dict(P2))
     os.chdir(tmp_path)
@@ -151,3 +155,69 @@ restart_interval = 200
     assert len(lines) == 1 + 460 and int(lines[-1].split()[0]) == 459
     vol = np.array([float(l.split()[1]) for l in lines[1:]])
     assert (np.diff(vol) <= 1e-9).all()
+
+
+def test_resumed_run_equals_uninterrupted_run(tmp_path, monkeypatch):
+    """230 + 230 iterations through a restart file write the same volumes.txt, line for line, as 460 iterations in one go
+    (same seed): the restart carries every walker's Philox counter and the step adaptation is a pure function of the
+    iteration number.  The restart file is also layout independent: written with ranks_per_gpu = 4, resumed with 2 x 12."""
+    from hans_b200 import NSio, mpihans
+    monkeypatch.chdir(tmp_path)
+    base = """move_ratio = 3,48,32,16,3,3
+nbeads = 4
+nchains = 8
+nwalkers = 6
+ranks_per_gpu = 4
+walklength = 3
+initial_walk = 10
+seed = 17
+restart_interval = 0
+traj_interval = 0
+"""
+    mpihans.main(dict(NSio.parse_hans_text(base + "iterations = 460\ndirectory = whole\n")))
+    os.chdir(tmp_path)
+    mpihans.main(dict(NSio.parse_hans_text(base + "iterations = 230\ndirectory = parts\n")))
+    os.chdir(tmp_path)
+    mpihans.main(dict(NSio.parse_hans_text("from_restart = 1\ndirectory = parts\n")))
+    os.chdir(tmp_path)
+    whole = open("whole/volumes.txt").read().splitlines()
+    parts = open("parts/volumes.txt").read().splitlines()
+    assert len(whole) == 461 and whole == parts
+    a1, w1 = NSio.open_restart("whole/restart.hdf5")
+    a2, w2 = NSio.open_restart("parts/restart.hdf5")
+    assert a1["prev_iters"] == a2["prev_iters"] == 460
+    for g in w1:
+        assert np.array_equal(w1[g][0], w2[g][0]) and np.array_equal(w1[g][1], w2[g][1]) and w1[g][2] == w2[g][2]
+    for k in ("dv_max", "dr_max", "dt_max", "dh_max", "dshear", "dstretch"):
+        assert a1[k] == a2[k]
+
+
+def test_initial_config_import(tmp_path, monkeypatch):
+    """`initial_config = file.extxyz` (mpihans.py:149-161): every walker starts from the given configuration."""
+    from common import make_walkers
+    from hans_b200 import NSio, mpihans
+    from hans_b200.atoms import Atoms, write_extxyz
+    monkeypatch.chdir(tmp_path)
+    cfg, H, R, kw = make_walkers("tiny", 1, seed=2)
+    write_extxyz(str(tmp_path / "start.extxyz"), Atoms("C12", positions=R[0], pbc=True, cell=H[0]), append=False)
+    text = """move_ratio = 1,18,12,0,3,3
+nbeads = 2
+nchains = 6
+nwalkers = 3
+ranks_per_gpu = 2
+iterations = 1
+walklength = 1
+initial_walk = 0
+directory = imp
+seed = 5
+initial_config = start.extxyz
+"""
+    ns = mpihans.main(dict(NSio.parse_hans_text(text)))
+    os.chdir(tmp_path)
+    attrs, walkers = NSio.open_restart("imp/restart.hdf5")
+    # one iteration walked one walker per virtual rank; the other four still hold the imported configuration
+    same = [g for g, w in walkers.items() if np.allclose(w[0], R[0], atol=1e-7) and np.allclose(w[1], H[0], atol=1e-7)]
+    assert len(walkers) == 6 and len(same) >= 4
+    bad = dict(NSio.parse_hans_text(text.replace("nchains = 6", "nchains = 5").replace("directory = imp", "directory = imp2")))
+    with pytest.raises(AssertionError):
+        mpihans.main(bad)

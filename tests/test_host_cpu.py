@@ -144,8 +144,17 @@ def test_restart_container_and_cleanup(tmp_path, monkeypatch):
     assert attrs["prev_iters"] == 50000 and attrs["dshear"] == 0.3 and attrs["nchains"] == 16          # NSio.py:74-83
     assert attrs["iterations"] == "800000" and list(attrs["move_ratio"]) == [3, 48, 32, 0, 3, 3]
     assert sorted(walkers) == ["walker_0_0001", "walker_0_0002", "walker_1_0001", "walker_1_0002"]    # NSio.py:87
-    c, u = walkers["walker_1_0002"]
+    c, u, ctr = walkers["walker_1_0002"]
+    assert ctr is None   # no counters were passed
     assert c.shape == (96, 3) and u.shape == (3, 3) and np.array_equal(c, states[1][1][1]) and np.array_equal(u, states[1][0][1])
+    # virtual ranks: one GPU holding 4 walkers = 2 ranks x nwalkers 2 writes the SAME groups as two GPUs with 2 each
+    one_gpu = [(np.concatenate([states[0][0], states[1][0]]), np.concatenate([states[0][1], states[1][1]]), np.arange(4) * 1000)]
+    NSio.write_to_restart(P, one_gpu, filename="restart_v.hdf5", i=49999, steps=steps, nwalkers=2)
+    _, wv = NSio.open_restart("restart_v.hdf5")
+    assert sorted(wv) == sorted(walkers)
+    for g in walkers:
+        assert np.array_equal(wv[g][0], walkers[g][0]) and np.array_equal(wv[g][1], walkers[g][1])
+    assert [wv[g][2] for g in sorted(wv)] == [0.0, 1000.0, 2000.0, 3000.0]   # Philox counters (dataset philox_ctr)
     # restart_cleanup, NSio.py:127-144
     with open("volumes.txt", "w") as f:
         f.write("40 1 64 False 16 \n")
