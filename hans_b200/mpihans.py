@@ -178,8 +178,11 @@ def main(SimParams, comm: "_Dist | None" = None):
     restart_walkers = None
     if from_restart:
         attrs, restart_walkers = NSio.open_restart(SimParams["restart_file"])  # mpihans.py:77-89
+        # `ranks_per_gpu` is this implementation's own key: if the resume input names it, it wins, so that a run can be
+        # resumed on another number of GPUs (the file is laid out per virtual rank); everything else comes from the file
+        keep = ("restart_file", "time") + (("ranks_per_gpu",) if "ranks_per_gpu" in SimParams else ())
         for k, v in attrs.items():
-            if k not in ("restart_file", "time"):
+            if k not in keep:
                 if isinstance(v, np.floating):
                     v = float(v)
                 elif isinstance(v, np.integer):
@@ -187,8 +190,14 @@ def main(SimParams, comm: "_Dist | None" = None):
                 elif isinstance(v, np.ndarray) and v.dtype.kind in "US":
                     v = str(v)
                 SimParams[k] = v
+        rpg = int(SimParams.get("ranks_per_gpu", 1))
+        size = world * rpg
+        if len(restart_walkers) != int(SimParams["nwalkers"]) * size:
+            raise ValueError(f"restart file holds {len(restart_walkers)} walkers = nwalkers {SimParams['nwalkers']} x "
+                             f"{len(restart_walkers) // max(int(SimParams['nwalkers']), 1)} ranks, but this run has {world} GPU(s) x "
+                             f"ranks_per_gpu {rpg}; set ranks_per_gpu so that GPUs x ranks_per_gpu matches (mpihans.py:171-179)")
         if rank == 0:
-            NSio.restart_cleanup(SimParams, TRAJ_INTERVAL)
+            NSio.restart_cleanup(SimParams, int(SimParams.get("traj_interval", TRAJ_INTERVAL)) or TRAJ_INTERVAL)
         comm.barrier()
     elif rank == 0:
         print("New Run")

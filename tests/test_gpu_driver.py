@@ -160,7 +160,7 @@ restart_interval = 200
 def test_resumed_run_equals_uninterrupted_run(tmp_path, monkeypatch):
     """230 + 230 iterations through a restart file write the same volumes.txt, line for line, as 460 iterations in one go
     (same seed): the restart carries every walker's Philox counter and the step adaptation is a pure function of the
-    iteration number.  The restart file is also layout independent: written with ranks_per_gpu = 4, resumed with 2 x 12."""
+    iteration number."""
     from hans_b200 import NSio, mpihans
     monkeypatch.chdir(tmp_path)
     base = """move_ratio = 3,48,32,16,3,3
@@ -178,7 +178,11 @@ traj_interval = 0
     os.chdir(tmp_path)
     mpihans.main(dict(NSio.parse_hans_text(base + "iterations = 230\ndirectory = parts\n")))
     os.chdir(tmp_path)
-    mpihans.main(dict(NSio.parse_hans_text("from_restart = 1\ndirectory = parts\n")))
+    ns2 = mpihans.main(dict(NSio.parse_hans_text("from_restart = 1\ndirectory = parts\n")))
+    os.chdir(tmp_path)
+    assert ns2.K == 24 and ns2.nvranks == 4   # ranks_per_gpu came back from the file
+    with pytest.raises(ValueError):           # 3 virtual ranks cannot hold a file of 4
+        mpihans.main(dict(NSio.parse_hans_text("from_restart = 1\ndirectory = parts\nranks_per_gpu = 3\n")))
     os.chdir(tmp_path)
     whole = open("whole/volumes.txt").read().splitlines()
     parts = open("parts/volumes.txt").read().splitlines()
