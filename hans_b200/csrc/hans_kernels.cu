@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 
 namespace hb {
@@ -386,11 +387,11 @@ static int check_cfg(const hans_cfg *c)
     return HANS_OK;
 }
 
-static size_t cta_smem_bytes(const hans_cfg *c, int T)
+static size_t cta_smem_bytes(const hans_cfg *c, int T, bool cells = false)
 {
     const int gpc = (T == 32) ? 4 : 1;
     const int N = c->nchains * c->nbeads;
-    return walker_smem_bytes(N, c->nbeads, T) * gpc + cta_extra_bytes(c->nbeads, c->nexclude);
+    return (walker_smem_bytes(N, c->nbeads, T) + (cells ? cell_smem_bytes(N) : 0)) * gpc + cta_extra_bytes(c->nbeads, c->nexclude);
 }
 
 static int sm_count()
@@ -585,26 +586,33 @@ int hans_default_team(const hans_cfg *cfg)
     return 0;
 }
 
-static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
+// Bead number density above which the cell-list kernel takes a walker over from the sphere-pruning kernels when
+// threads_per_walker = 0 (measured crossover, profiles/r02_cells_*; HANS_RHO_SPLIT overrides it for measurements)
+static double rho_split()
+{
+    static double v = -1.0;
+    if (v < 0.0) {
+        const char *e = getenv("HANS_RHO_SPLIT");
+        v = e ? atof(e) : 0.30;
+    }
+    return v;
+}
+
+// threads per walker of the cell-list kernel for a shape
+static int cells_T(const hans_cfg *c)
+{
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("HANS_CELLS_T"); forced = e ? atoi(e) : 0; }
+    if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+    const int N = c->nchains * c->nbeads;
+    return N <= 128 ? 32 : (N <= 1024 ? 128 : 256);
+}
+
+// the cooperative kernel (all threads of a walker's group share every move), optionally with the per-walker cell list
+static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory, int T, cudaStream_t st)
 {
     int rc = HANS_OK;
-    if (threads_per_walker == 0 && a.mode == HANS_MODE_FUSED && !lean_applies(cfg) && hans_default_team(cfg))
-        threads_per_walker = 20 + hans_default_team(cfg);
-    if ((threads_per_walker == 24 || threads_per_walker == 28) && a.mode == HANS_MODE_FUSED) {
-        const int nwarp = threads_per_walker - 20;
-        if (!team_applies(cfg, nwarp))
-            return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
-        return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
-    }
-    if (threads_per_walker < 24 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
-        const int W = pick_W(cfg, threads_per_walker);
-        if (W > 0) return from_memory ? launch_lean<true>(a, W, st) : launch_lean<false>(a, W, st);
-        if (threads_per_walker != 0)
-            return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
-    }
-    const int T = pick_T(cfg, threads_per_walker);
-    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 24, 28, 32, 64, 128 or 256");
-    const size_t smem = cta_smem_bytes(cfg, T);
+    const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode != 0);
     if (from_memory) {
         DISPATCH_T(T, {
             rc = prep_kernel(walk_kernel<TT, true>, smem);
@@ -620,6 +628,60 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
     }
     CK(cudaGetLastError());
     return HANS_OK;
+}
+
+// does the cell-list kernel fit shared memory for this shape (with T threads per walker)?
+static bool cells_fit(const hans_cfg *cfg, int T) { return cta_smem_bytes(cfg, T, true) <= 227 * 1024; }
+
+static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
+{
+    const bool want_cells = (threads_per_walker & HANS_TPW_CELLS) != 0;
+    threads_per_walker &= ~HANS_TPW_CELLS;
+    if (want_cells) { // explicit: the cooperative kernel with the cell list for every walker
+        const int T = threads_per_walker == 0 ? cells_T(cfg) : pick_T(cfg, threads_per_walker);
+        if (T < 0 || threads_per_walker == 1 || threads_per_walker == 8 || threads_per_walker == 24 || threads_per_walker == 28)
+            return fail(HANS_EINVAL, "HANS_TPW_CELLS goes with threads_per_walker 0, 32, 64, 128 or 256");
+        a.cells_mode = 1;
+        return launch_coop(cfg, a, from_memory, T, st);
+    }
+    const bool dflt = threads_per_walker == 0;
+    if (dflt && a.mode == HANS_MODE_FUSED && !lean_applies(cfg) && hans_default_team(cfg))
+        threads_per_walker = 20 + hans_default_team(cfg);
+    if ((threads_per_walker == 24 || threads_per_walker == 28) && a.mode == HANS_MODE_FUSED) {
+        const int nwarp = threads_per_walker - 20;
+        if (!team_applies(cfg, nwarp))
+            return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
+        if (dflt && cells_fit(cfg, cells_T(cfg)) && rho_split() > 0.0) {
+            // default for large chain systems: two launches share the walk -- the warp-per-move kernel takes the walkers
+            // below the density split, the cell-list kernel the dense ones (where bounding spheres prune nothing)
+            WalkArgs lo = a, hi = a;
+            unsigned char *flags = nullptr;
+            CK(cudaMallocAsync((void **)&flags, (size_t)a.n_active, st));
+            classify_kernel<<<(a.n_active + 127) / 128, 128, 0, st>>>(a.H, a.ids, a.n_active, cfg->nchains * cfg->nbeads, rho_split(), flags);
+            lo.gate = 1; hi.gate = 2;
+            lo.gate_flags = hi.gate_flags = flags;
+            lo.rho_split = hi.rho_split = rho_split();
+            hi.cells_mode = 1;
+            int rc = from_memory ? launch_team<true>(lo, nwarp, st) : launch_team<false>(lo, nwarp, st);
+            if (rc == HANS_OK) rc = launch_coop(cfg, hi, from_memory, cells_T(cfg), st);
+            cudaFreeAsync(flags, st);
+            return rc;
+        }
+        return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
+    }
+    if (threads_per_walker < 24 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
+        const int W = pick_W(cfg, threads_per_walker);
+        if (W > 0) return from_memory ? launch_lean<true>(a, W, st) : launch_lean<false>(a, W, st);
+        if (threads_per_walker != 0)
+            return fail(HANS_ELIMIT, "the warp-per-walker kernel (threads_per_walker 1, 8) needs nchains*nbeads <= 128 and nbeads in {1,2,4,6,8,12}");
+    }
+    const int T = pick_T(cfg, threads_per_walker);
+    if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 24, 28, 32, 64, 128 or 256 (optionally | HANS_TPW_CELLS)");
+    if (dflt && cfg->nchains * cfg->nbeads >= 192 && cells_fit(cfg, T) && rho_split() > 0.0) {
+        a.cells_mode = 2; // shapes that run on this kernel by default: the cell list per walker, above the density split
+        a.rho_split = rho_split();
+    }
+    return launch_coop(cfg, a, from_memory, T, st);
 }
 
 static int gen_launch(const hans_cfg *cfg, const uint64_t *d_ctr, uint64_t ctr_off, const int32_t *d_ids, int n_active,

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     for (int k = blockIdx.x; k < a.n_active; k += gridDim.x) {
         const int wi = a.ids ? a.ids[k] : k;
+        if (gate_skips(a, k)) continue; // (uniform over the CTA)
         load_walker<T>(w, a.H, a.R, wi, true);
         Filt f = load_filt(W_SF(w));
         const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];

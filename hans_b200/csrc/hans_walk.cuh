@@ -67,6 +67,8 @@ struct WCtx {
     int w4;   //                                      float4 index of their shadows [W][nb]
     int rad;  // float index of the chain bounding radii RAD[nc]
     int lst;  // int index of the near list LST[T] (+ its counter at lst - 1 ... see near_list())
+    int cl;   // int index of the per-walker cell list area (cell_smem_bytes), behind the window area / tail
+    int cells; // != 0: overlap tests go through the cell list (set per walker by the kernels that carry the area)
     unsigned nbmagic, ncmagic; // x / nb = umulhi(x, nbmagic), x / nc = umulhi(x, ncmagic) for x < 2^16
 };
 #define W_P(w) ((w).D0)
@@ -117,8 +119,22 @@ __host__ __device__ inline size_t window_smem_bytes(int nb, int W)
     return (((size_t)W * nb * 40) + 63) & ~(size_t)63;
 }
 
+// Per-walker cell list (the role of hs_alkane's link cells, which the reference bypasses at MCNS.py:603): bins in
+// FRACTIONAL space, n_k = floor(w_k / 1.001) per axis (w_k = perpendicular width of the cell along axis k), capped at
+// CL_M per axis.  Layout (ints): dims[8] = {n0, n1, n2, nbins} of the current cell and of the trial cell of a box
+// move; head[CL_CAP], head2[CL_CAP] (first bead of each bin, -1 = empty); next[N], next2[N] (singly linked).
+constexpr int CL_M = 10;
+constexpr int CL_CAP = CL_M * CL_M * CL_M;
+__host__ __device__ inline size_t cell_smem_bytes(int N) { return (4 * ((size_t)8 + 2 * CL_CAP + 2 * (size_t)N) + 63) & ~(size_t)63; }
+#define CL_DIMS(w) ((w).cl)
+#define CL_HEAD(w) ((w).cl + 8)
+#define CL_HEAD2(w) ((w).cl + 8 + CL_CAP)
+#define CL_NEXT(w) ((w).cl + 8 + 2 * CL_CAP)
+#define CL_NEXT2(w) ((w).cl + 8 + 2 * CL_CAP + (w).N)
+#define SMI (reinterpret_cast<int *>(smem))
+
 // GPC walker groups of T threads per CTA; W > 0 adds the window area behind each walker's ring, `tail` bytes
-// (a multiple of 64) behind that
+// (a multiple of 64) behind that (the warp-per-move kernel's scratch, or the cell list of walk_kernel)
 template <int T, int GPC>
 __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail = 0)
 {
@@ -143,6 +159,8 @@ __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail =
     w.ncmagic = 0xFFFFFFFFu / (unsigned)w.nc + 1u;
     w.wc = (base + core) / 8;
     w.w4 = (base + core + 24 * W * w.nb + 15) / 16;
+    w.cl = (base + core + (int)window_smem_bytes(w.nb, W)) / 4;
+    w.cells = 0;
     const int extra = per * GPC;
     w.cfg = extra / 8;
     w.itab = (extra + (int)((sizeof(hans_cfg) + 15) & ~(size_t)15)) / 2;
@@ -161,9 +179,9 @@ __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail =
     return w;
 }
 
-template <int T> __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c)
+template <int T> __device__ __forceinline__ WCtx setup_ctx(const hans_cfg &c, int tail = 0)
 {
-    return setup_ctx_g<T, cta_threads<T>() / T>(c, 0);
+    return setup_ctx_g<T, cta_threads<T>() / T>(c, 0, tail);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -460,6 +478,93 @@ template <int T> __device__ __forceinline__ void coop_reset(const WCtx &w)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-walker cell list (layout at cell_smem_bytes).
+//
+// Correctness: the decision is the single-image float64 r^2 < 1 (pair_r2).  For such a pair the wrapped fractional
+// difference ds = d.H^-1 obeys |ds_k| <= |d| / w_k < 1 / w_k, and a bin is at least 1.001 / w_k wide, so the two beads sit
+// in the same or in adjacent bins (periodically) along every axis -- also when the wrapped image is not the nearest one.
+// Bins are computed from the float32 shadows (wrapped fractional coordinates, error 2^-24): the 0.1 % margin of the
+// bin width covers that for every cell narrower than ~10^4 sigma.  So the beads found in the <= 27 bins around a
+// bead are a superset of its overlap partners: decisions are those of the all-pairs test, bit for bit.  Axes with fewer
+// than three bins enumerate each bin once.
+// ---------------------------------------------------------------------------------------------
+struct Grid { int n0, n1, n2; };
+__device__ __forceinline__ Grid load_grid(int dims) { Grid g; g.n0 = SMI[dims]; g.n1 = SMI[dims + 1]; g.n2 = SMI[dims + 2]; return g; }
+__device__ __forceinline__ int cl_coord(float s, int n)
+{
+    int b = (int)((s + 0.5f) * (float)n);
+    b = b < 0 ? 0 : b;
+    return b >= n ? n - 1 : b;
+}
+__device__ __forceinline__ int cl_bin(const Grid &g, const float4 s)
+{
+    return (cl_coord(s.x, g.n0) * g.n1 + cl_coord(s.y, g.n1)) * g.n2 + cl_coord(s.z, g.n2);
+}
+// neighbour o (0 .. min(n,3)-1) of coordinate b along an axis of n bins
+__device__ __forceinline__ int cl_nbr(int b, int o, int n)
+{
+    int x = b + o - (n >= 3 ? 1 : 0);
+    x = x < 0 ? x + n : x;
+    return x >= n ? x - n : x;
+}
+
+// grid of the cell whose inverse is at smem[hi]; written to dims by one thread
+__device__ __noinline__ void cl_dims(int hi, int dims)
+{
+    const double *Hi = smem + hi;
+    const double b0 = (Hi[0] * Hi[0] + Hi[3] * Hi[3]) + Hi[6] * Hi[6]; // 1 / w_0^2
+    const double b1 = (Hi[1] * Hi[1] + Hi[4] * Hi[4]) + Hi[7] * Hi[7];
+    const double b2 = (Hi[2] * Hi[2] + Hi[5] * Hi[5]) + Hi[8] * Hi[8];
+    int n[3];
+    const double bb[3] = {b0, b1, b2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double wk = 1.0 / sqrt(bb[k]);
+        double q = floor(wk / 1.001);
+        q = q < 1.0 ? 1.0 : (q > (double)CL_M ? (double)CL_M : q);
+        n[k] = (int)q;
+    }
+    SMI[dims] = n[0]; SMI[dims + 1] = n[1]; SMI[dims + 2] = n[2]; SMI[dims + 3] = n[0] * n[1] * n[2];
+}
+
+// (re)build a list from the shadows at q4 under the inverse cell at smem[hi]; collective, ends with a group barrier
+template <int T>
+__device__ __noinline__ void cl_build(WCtx w, int hi, int q4, int dims, int head, int next)
+{
+    if (w.lane == 0) cl_dims(hi, dims);
+    gsync<T>();
+    const Grid g = load_grid(dims);
+    const int nbins = g.n0 * g.n1 * g.n2;
+#pragma unroll 1
+    for (int b = w.lane; b < nbins; b += T) SMI[head + b] = -1;
+    gsync<T>();
+#pragma unroll 1
+    for (int i = w.lane; i < w.N; i += T) SMI[next + i] = atomicExch(SMI + head + cl_bin(g, SM4[q4 + i]), i);
+    gsync<T>();
+}
+
+// the chain's beads [b0, nb) leave the bins of their old shadows (F4) and enter those of the trial shadows (C4);
+// one thread: concurrent unlinking is not safe, and a chain is a handful of beads.  Call BEFORE F4 is overwritten.
+__device__ __noinline__ void cl_move_chain(WCtx w, int ichain, int b0)
+{
+    const Grid g = load_grid(CL_DIMS(w));
+    const int head = CL_HEAD(w), next = CL_NEXT(w), c0 = ichain * w.nb;
+#pragma unroll 1
+    for (int b = b0; b < w.nb; ++b) {
+        const int i = c0 + b;
+        const int bo = cl_bin(g, SM4[W_F4(w) + i]), bn = cl_bin(g, SM4[W_C4(w) + b]);
+        if (bo == bn) continue;
+        int j = SMI[head + bo], prev = -1;
+        while (j != i && j >= 0) { prev = j; j = SMI[next + j]; }
+        if (j == i) {
+            if (prev < 0) SMI[head + bo] = SMI[next + i]; else SMI[next + prev] = SMI[next + i];
+        }
+        SMI[next + i] = SMI[head + bn];
+        SMI[head + bn] = i;
+    }
+}
+
 // Does the trial chain (CN / C4, bounding radius Rt) overlap anything?  NB > 0: beads per chain known
 // at compile time, trial shadows in registers.
 template <int T, int NB>
@@ -576,6 +681,66 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
     }
 }
 
+// Does the trial chain (CN / C4) overlap anything?  Cell-list version: one task per (moved trial bead, neighbour bin),
+// spread over the group's threads; every bead found there that belongs to another chain goes through the float32
+// filter.  Same votes and the same float64 settle as chain_overlaps_pruned.
+template <int T>
+__device__ __forceinline__ bool chain_overlaps_cells(const WCtx &w, const Filt &f, int ichain, int b0, bool intra, unsigned &pairs)
+{
+    const Grid g = load_grid(CL_DIMS(w));
+    const int nb = w.nb, c0 = ichain * nb, f4 = W_F4(w), c4 = W_C4(w), head = CL_HEAD(w), next = CL_NEXT(w);
+    const int k0 = g.n0 < 3 ? g.n0 : 3, k1 = g.n1 < 3 ? g.n1 : 3, k2 = g.n2 < 3 ? g.n2 : 3;
+    const int k12 = k1 * k2, K = k0 * k12, ntask = (nb - b0) * K;
+    bool ov = false, amb = false;
+#pragma unroll 1
+    for (int t = w.lane; t < ntask; t += T) {
+        const int bi = t / K, o = t - bi * K;
+        const int o0 = o / k12, o1 = (o - o0 * k12) / k2, o2 = o - o0 * k12 - o1 * k2;
+        const float4 tb = SM4[c4 + b0 + bi];
+        const int bin = (cl_nbr(cl_coord(tb.x, g.n0), o0, g.n0) * g.n1 + cl_nbr(cl_coord(tb.y, g.n1), o1, g.n1)) * g.n2 +
+                        cl_nbr(cl_coord(tb.z, g.n2), o2, g.n2);
+#pragma unroll 1
+        for (int j = SMI[head + bin]; j >= 0; j = SMI[next + j]) {
+            if ((unsigned)(j - c0) < (unsigned)nb) continue;
+            const float4 sj = SM4[f4 + j];
+            const float r2 = r2_f32(f, sj.x - tb.x, sj.y - tb.y, sj.z - tb.z);
+            ov |= (r2 < f.lo);
+            amb |= !(r2 > f.hi);
+            pairs += 1u;
+        }
+    }
+    bool amb_intra = false;
+    if (intra) {
+        const uchar2 *tab = W_ITAB(w);
+        for (int e = w.lane; e < w.npc; e += T) {
+            const uchar2 jb = tab[e];
+            if ((int)jb.y >= b0) {
+                const float4 p = SM4[c4 + jb.x], q = SM4[c4 + jb.y];
+                const float r2 = r2_f32(f, q.x - p.x, q.y - p.y, q.z - p.z);
+                ov |= (r2 < f.lo);
+                amb_intra |= !(r2 > f.hi);
+                pairs += 1;
+            }
+        }
+    }
+    if (T == 32) {
+        const unsigned code = __reduce_or_sync(FULL, (ov ? 4u : 0u) | (amb ? 1u : 0u) | (amb_intra ? 2u : 0u));
+        if (code & 4u) return true;
+        if (code) return __any_sync(FULL, recheck_chain_exact<T>(w, ichain, b0, (code & 1u) != 0u, (code & 2u) != 0u));
+        return false;
+    }
+    {   // T > 32: one barrier for the three flags (the caller zeroed the vote word, coop_reset)
+        int *vote = reinterpret_cast<int *>(smem) + w.lst - 3;
+        const unsigned wcode = __reduce_or_sync(FULL, (ov ? 4u : 0u) | (amb ? 1u : 0u) | (amb_intra ? 2u : 0u));
+        if ((threadIdx.x & 31) == 0 && wcode) atomicOr(vote, (int)wcode);
+        __syncthreads();
+        const unsigned code = (unsigned)*vote;
+        if (code & 4u) return true;
+        if (code) return gany<T>(recheck_chain_exact<T>(w, ichain, b0, (code & 1u) != 0u, (code & 2u) != 0u));
+        return false;
+    }
+}
+
 // translate / rotate / dihedral: alk.alkane_translate_chain, alkane_rotate_chain,
 // alkane_bond_rotate (MCNS.py:323,328,333) + accept/restore (MCNS.py:371-380)
 template <int T>
@@ -590,14 +755,20 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
     gsync<T>();
     bool ov;
     float Rt = 0.0f;
-    if (nb > 1) {
-        Rt = intra ? chain_radius(cn, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
+    if (nb > 1) Rt = intra ? chain_radius(cn, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
+    if (w.cells) {
+        ov = chain_overlaps_cells<T>(w, load_filt(W_SF(w)), ichain, b0, intra, pairs);
+    } else if (nb > 1) {
         ov = chain_overlaps_pruned<T, 0>(w, load_filt(W_SF(w)), ichain, b0, intra, Rt, pairs);
     } else {
         ov = chain_overlaps<T>(w, ichain, b0, intra, pairs);
     }
     const double boltz = ov ? 0.0 : 1.0;
     if ((mode == HANS_MODE_PROPOSE) || (p->u_acc < boltz)) { // MCNS.py:372
+        if (w.cells) { // (every thread is past its reads of the list: the vote above was a group barrier)
+            if (w.lane == 0) cl_move_chain(w, ichain, b0);
+            gsync<T>();
+        }
         const int f4 = W_F4(w) + c0;
         for (int b = w.lane; b < nb; b += T) {
             smem[P + 3 * b] = smem[cn + 3 * b]; smem[P + 3 * b + 1] = smem[cn + 3 * b + 1]; smem[P + 3 * b + 2] = smem[cn + 3 * b + 2];
@@ -661,6 +832,74 @@ __device__ __noinline__ bool trial_overlap_exact(WCtx w, bool with_intra)
 #pragma unroll
     for (int k = 0; k < 9; ++k) { H[k] = smem[W_SH(w) + 18 + k]; Hi[k] = smem[W_SH(w) + 27 + k]; }
     return all_overlap64<T>(w, W_TP(w), H, Hi, with_intra);
+}
+
+// All pairs of the TRIAL beads (TP / G4 under the trial cell) through a cell list built for the trial cell: one task
+// per (bead i, neighbour bin), pairs (i, j > i) only so that every pair is tested once; same-chain pairs only if
+// with_intra and further apart than nexclude.  A vote every CL_VOTE tasks per thread ends a rejected move early.
+// Pairs inside the filter's band: the first one per thread is settled in float64, more than one -> the full float64 pass.
+#define CL_VOTE 8
+template <int T>
+__device__ __forceinline__ bool trial_overlap_cells(const WCtx &w, bool with_intra, unsigned &pairs)
+{
+    cl_build<T>(w, W_SH(w) + 27, W_G4(w), CL_DIMS(w) + 4, CL_HEAD2(w), CL_NEXT2(w));
+    const Filt f = load_filt(W_SF(w) + SF_TRIAL);
+    const Grid g = load_grid(CL_DIMS(w) + 4);
+    const int nb = w.nb, N = w.N, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18, head = CL_HEAD2(w), next = CL_NEXT2(w);
+    const int k0 = g.n0 < 3 ? g.n0 : 3, k1 = g.n1 < 3 ? g.n1 : 3, k2 = g.n2 < 3 ? g.n2 : 3;
+    const int k12 = k1 * k2, K = k0 * k12, ntask = N * K;
+    const int nex_eff = with_intra ? w.nex : 0x3fffffff;
+    bool ov = false;
+    int namb = 0, ai = 0, aj = 0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < ntask; t0 += T * CL_VOTE) {
+#pragma unroll 1
+        for (int u = 0; u < CL_VOTE; ++u) {
+            const int t = t0 + u * T + w.lane;
+            if (t < ntask) {
+                const int i = t / K, o = t - i * K;
+                const int o0 = o / k12, o1 = (o - o0 * k12) / k2, o2 = o - o0 * k12 - o1 * k2;
+                const float4 si = SM4[g4 + i];
+                const int bin = (cl_nbr(cl_coord(si.x, g.n0), o0, g.n0) * g.n1 + cl_nbr(cl_coord(si.y, g.n1), o1, g.n1)) * g.n2 +
+                                cl_nbr(cl_coord(si.z, g.n2), o2, g.n2);
+                const int ci0 = div_nb(w, i) * nb;
+#pragma unroll 1
+                for (int j = SMI[head + bin]; j >= 0; j = SMI[next + j]) {
+                    if (j <= i) continue;
+                    if ((unsigned)(j - ci0) < (unsigned)nb && (j - i) <= nex_eff) continue; // same chain, excluded
+                    const float4 sj = SM4[g4 + j];
+                    const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
+                    ov |= (r2 < f.lo);
+                    if (!(r2 < f.lo) && !(r2 > f.hi)) {
+                        if (namb == 0) { ai = i; aj = j; }
+                        ++namb;
+                    }
+                    pairs += 1u;
+                }
+            }
+        }
+        if (gany<T>(ov)) return true;
+    }
+    if (gany<T>(namb > 0)) {
+        if (namb > 0)
+            ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj] - smem[tp + 3 * ai], smem[tp + 3 * aj + 1] - smem[tp + 3 * ai + 1],
+                          smem[tp + 3 * aj + 2] - smem[tp + 3 * ai + 2]) < 1.0;
+        if (gany<T>(ov)) return true;
+        if (gany<T>(namb > 1)) return trial_overlap_exact<T>(w, with_intra);
+    }
+    return false;
+}
+
+// the trial list becomes the current one (accepted box move)
+template <int T> __device__ __forceinline__ void cl_commit_trial(const WCtx &w)
+{
+    const int n = SMI[CL_DIMS(w) + 7];
+#pragma unroll 1
+    for (int b = w.lane; b < n; b += T) SMI[CL_HEAD(w) + b] = SMI[CL_HEAD2(w) + b];
+#pragma unroll 1
+    for (int i = w.lane; i < w.N; i += T) SMI[CL_NEXT(w) + i] = SMI[CL_NEXT2(w) + i];
+    if (w.lane < 4) SMI[CL_DIMS(w) + w.lane] = SMI[CL_DIMS(w) + 4 + w.lane];
+    gsync<T>();
 }
 
 // Box moves of chain systems: all pairs of CHAINS through their bounding spheres (round robin over
@@ -764,6 +1003,7 @@ template <int T>
 __device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
 {
     if (w.nc == 1) return trial_overlap_exact<T>(w, with_intra);
+    if (w.cells) return trial_overlap_cells<T>(w, with_intra, pairs);
     if (w.nb > 1) return trial_overlap_pruned<T>(w, with_intra, pairs);
     const Filt f = load_filt(W_SF(w) + SF_TRIAL);
     const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w);
@@ -952,6 +1192,11 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
     if (reason == HANS_ACCEPT && trial_overlap<T>(w, !is_vol, out.pairs)) reason = HANS_REJ_OVERLAP; // MCNS.py:198,247
     if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
         commit_trial<T>(w);
+        if (w.cells) {
+            // (a shape rejection or a single-chain walker never built the trial list)
+            if (reason == HANS_REJ_ASPECT || reason == HANS_REJ_ANGLE || w.nc == 1) cl_build<T>(w, sh + 9, W_F4(w), CL_DIMS(w), CL_HEAD(w), CL_NEXT(w));
+            else cl_commit_trial<T>(w);
+        }
     } else if (!is_vol) {
         // MCNS.py:366-368: the reference reverts by applying -dH through alkane_change_box, which
         // is not an exact restore; reproduce that arithmetic from the trial state.  (A rejected
@@ -969,6 +1214,7 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         follow_cell<T>(w, W_TP(w), W_P(w), W_F4(w), sh + 27, sh, sh + 9);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
+        if (w.cells) cl_build<T>(w, sh + 9, W_F4(w), CL_DIMS(w), CL_HEAD(w), CL_NEXT(w)); // the shadows were recomputed
     }
     out.accepted = reason == HANS_ACCEPT; out.reason = reason;
     out.boltz = reason == HANS_ACCEPT ? (is_vol ? boltz_f : 1.0) : 0.0;
@@ -1003,6 +1249,7 @@ __device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, con
             for (int c = w.lane; c < w.nc; c += T) SMF[w.rad + c] = chain_radius(p + 3 * c * w.nb, w.nb);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
+        if (w.cells) cl_build<T>(w, sh + 9, f4, CL_DIMS(w), CL_HEAD(w), CL_NEXT(w));
     }
 }
 
@@ -1040,20 +1287,55 @@ struct WalkArgs {
     int mode;
     int team_res; // warp-per-move kernel: int offset of its tail area in shared memory (set by the launcher)
     unsigned long long ctr_add; // proposals from memory: what the walk adds to the walkers' proposal counters
+    // Density gate: one walk may be served by two launches, each taking the walkers on its side of rho_split (bead
+    // number density N / V at the start of the walk, classified ONCE into gate_flags[k] by classify_kernel before the
+    // first of the two launches): 0 = every walker, 1 = only the dilute side (flag 0), 2 = only the dense side (flag 1).
+    // A skipped walker is not touched (state, counters, volume).
+    int gate;
+    const unsigned char *gate_flags;
+    // walk_kernel: 0 = no cell list, 1 = cell list for every walker, 2 = per walker, iff rho >= rho_split
+    int cells_mode;
+    double rho_split;
 };
+
+__device__ __forceinline__ double walker_density(const WalkArgs &a, int wi, int N)
+{
+    double H[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = a.H[(size_t)wi * 9 + k];
+    return (double)N / fabs(det3(H));
+}
+__device__ __forceinline__ bool gate_skips(const WalkArgs &a, int k)
+{
+    if (a.gate == 0) return false;
+    return (a.gate == 2) != (a.gate_flags[k] != 0);
+}
+
+// gate_flags[k] = walker ids[k] is on the dense side of the split
+__global__ void classify_kernel(const double *gH, const int32_t *ids, int n, int N, double rho_split, unsigned char *flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int wi = ids ? ids[k] : k;
+    double H[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) H[q] = gH[(size_t)wi * 9 + q];
+    flags[k] = !((double)N / fabs(det3(H)) < rho_split) ? 1 : 0;
+}
 
 template <int T, bool REPLAY>
 __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a)
 {
     constexpr int GPC = cta_threads<T>() / T;
-    const WCtx w = setup_ctx<T>(a.cfg);
+    WCtx w = setup_ctx<T>(a.cfg, a.cells_mode ? (int)cell_smem_bytes(a.cfg.nchains * a.cfg.nbeads) : 0);
     const int g = threadIdx.x / T;
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     const int mode = a.mode;
     for (int k0 = blockIdx.x * GPC; k0 < a.n_active; k0 += gridDim.x * GPC) {
         const int k = k0 + g;
-        if (k < a.n_active) {
+        if (k < a.n_active && !gate_skips(a, k)) {
             const int wi = a.ids ? a.ids[k] : k;
+            w.cells = a.cells_mode == 1 || (a.cells_mode == 2 && !(walker_density(a, wi, w.N) < a.rho_split));
             load_walker<T>(w, a.H, a.R, wi, true);
             const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
             unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0}; // this lane's share

@@ -56,6 +56,13 @@ enum {
 
 #define HANS_MAX_BEADS 64 /* beads per chain */
 
+/* OR-ed into threads_per_walker (0, 32, 64, 128, 256): the cooperative kernel with the PER-WALKER CELL LIST -- bins in
+ * fractional space at least 1.001 sigma wide in every direction, overlap candidates of a bead = the beads of the <= 27
+ * bins around it (the role of hs_alkane's link cells, bypassed by the reference at MCNS.py:603).  Same decisions and
+ * trajectories as every other kernel, bit for bit.  With threads_per_walker = 0 the library uses it by itself for
+ * walkers whose bead number density N / V exceeds the measured crossover (dense regime: bounding spheres prune nothing). */
+#define HANS_TPW_CELLS 4096
+
 /* Model + move parameters.  Replaces hs_alkane's module state set through
  * alkane_set_nchains/nbeads/bondlength/bondangle, alkane_set_d{v,r,t,h}_max (MCNS.py:599-606,
  * mpihans.py:118-133) and the MC_run arguments (MCNS.py:276-277). */
@@ -129,8 +136,10 @@ int hans_default_team(const hans_cfg *cfg);
  *                     4 / 8 warps per walker, up to 4 / 8 consecutive single-chain moves of distinct
  *                     chains evaluated at once, one warp each, and settled in order (same decisions
  *                     and trajectory, bit for bit); box moves are shared by the whole CTA;
+ *                     any of 0, 32, 64, 128, 256 | HANS_TPW_CELLS: cooperative kernel with the per-walker cell list;
  *                     0 = the measured default per shape: hans_default_window if non-zero, else
- *                     hans_default_team if non-zero, else hans_default_threads_per_walker.
+ *                     hans_default_team if non-zero, else hans_default_threads_per_walker -- and, for walkers of 192
+ *                     beads and more, the cell-list kernel for the walkers above the density crossover.
  *                     Every variant produces the same trajectory; the choice is speed only.
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,

@@ -1,0 +1,161 @@
+"""The per-walker cell list (BASELINE.json north_star; the link cells the reference bypasses at
+/root/reference/NesSa/MCNS.py:603): decisions and trajectories must equal the all-pairs oracle's, bit for bit, in the
+dilute regime, in the dense regime (where bounding spheres prune nothing), in thin / sheared cells (axes with fewer than
+three bins), with explicit proposals and self-driving, and when a walk is SHARED between the warp-per-move kernel
+(dilute walkers) and the cell-list kernel (dense walkers) by the default dispatch."""
+import numpy as np
+import pytest
+
+from common import SHAPES, compress, make_walkers
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+CELLS = 4096  # HANS_TPW_CELLS
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hans_b200 import engine
+    return engine
+
+
+def make_pool(eng, shape, H, R, kw, seed=0, tpw=0):
+    nchains, nbeads, mr = SHAPES[shape]
+    pool = eng.WalkerPool(H.shape[0], nchains, nbeads, mr, seed=seed, threads_per_walker=tpw, **kw)
+    pool.set_state(H, R)
+    return pool
+
+
+def assert_state_equal(pool, H, R):
+    gH, gR = pool.get_state()
+    assert np.array_equal(gH.view(np.uint64), H.view(np.uint64)), "cell differs from oracle"
+    bad = np.nonzero((gR.view(np.uint64) != R.view(np.uint64)).any(axis=(1, 2)))[0]
+    assert bad.size == 0, f"bead coordinates differ from oracle for walkers {bad[:8]}"
+
+
+def _replay(eng, oracle, shape, tpw, nwalkers=8, nmoves=400, seed=21, dense=None, mode=0, squash=None, **kw):
+    cfg, H, R, k = make_walkers(shape, nwalkers, seed=seed, **kw)
+    if dense:
+        H, R = compress(cfg, H, R, dense, seed)
+    if squash is not None:   # affine squash of cell and beads along one axis would overlap; shear instead (volume kept)
+        for w in range(nwalkers):
+            oracle.change_box(cfg, H[w], R[w], squash(w, H[w]))
+    props = np.stack([oracle.gen_proposals(cfg, 99, w, 0, nmoves) for w in range(nwalkers)])
+    limit = float(np.max([oracle.volume(H[w]) for w in range(nwalkers)]))
+    pool = make_pool(eng, shape, H, R, k, tpw=tpw)
+    got = pool.replay(None, props, volume_limit=limit, mode=mode)
+    want = np.stack([oracle.replay(cfg, H[w], R[w], props[w], limit, mode) for w in range(nwalkers)])
+    for f in ("accepted", "reason"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["boltz"].view(np.uint64), want["boltz"].view(np.uint64))
+    assert_state_equal(pool, H, R)
+    return props, want
+
+
+@pytest.mark.parametrize("shape,T", [("C1", 0), ("C1", 32), ("C1", 64), ("C2", 0), ("C2", 128), ("C4s", 0), ("C4s", 256),
+                                     ("dimer", 32), ("tiny", 0), ("tiny", 64), ("tiny1", 0), ("tiny1", 32), ("p7", 64),
+                                     ("t3", 128), ("h15", 0), ("d40", 64), ("d140", 128)])
+def test_cells_replay_all_moves(eng, oracle, shape, T):
+    nchains, nbeads, _ = SHAPES[shape]
+    SHAPES["_tmp"] = (nchains, nbeads, [1, 1, 1, 1 if nbeads >= 4 else 0, 1, 1])
+    try:
+        props, dec = _replay(eng, oracle, "_tmp", CELLS | T)
+    finally:
+        del SHAPES["_tmp"]
+    assert set(np.unique(props["type"])) >= ({0, 1, 2, 4, 5} if nbeads > 1 else {0, 1, 4, 5})
+    assert 0 < dec["accepted"].mean() < 1
+
+
+@pytest.mark.parametrize("shape,T,density", [("C1", 0, 0.45), ("C1", 64, 0.3), ("C2", 0, 0.7), ("C2", 32, 0.7), ("C4s", 128, 0.4),
+                                             ("dimer", 0, 0.5), ("d40", 64, 0.3), ("h15", 128, 0.25), ("p7", 0, 0.3),
+                                             ("tiny", 32, 0.5), ("t3", 0, 0.3)])
+def test_cells_replay_dense(eng, oracle, shape, T, density):
+    """Dense regime: cells a few diameters wide (2-4 bins per axis), most moves rejected by overlap."""
+    nchains, nbeads, _ = SHAPES[shape]
+    SHAPES["_tmp"] = (nchains, nbeads, [2, 6, 6 if nbeads > 1 else 0, 3 if nbeads >= 4 else 0, 2, 2])
+    try:
+        props, dec = _replay(eng, oracle, "_tmp", CELLS | T, nwalkers=6, nmoves=500, dense=density, dr_max=0.25, dt_max=0.3,
+                             dh_max=0.3, dv_max=2.0, dshear=0.1, dstretch=0.05)
+    finally:
+        del SHAPES["_tmp"]
+    assert (dec["reason"] == 1).mean() > 0.02 and dec["accepted"].mean() > 0.05
+
+
+@pytest.mark.parametrize("T", [0, 32, 128])
+def test_cells_thin_and_sheared_cells(eng, oracle, T):
+    """Strongly sheared cells (perpendicular widths down to ~2 sigma: one or two bins along an axis, where the wrapped
+    image need not be the nearest one) -- the list must still return every partner the single-image test flags."""
+    def shear(w, H):
+        d = np.zeros((3, 3))
+        d[0] = (0.9 + 0.2 * w) * H[1] + 0.4 * H[2]     # a += 0.9..1.9 b + 0.4 c : volume kept, widths shrink
+        d[2] = -0.5 * H[1]
+        return d
+    props, dec = _replay(eng, oracle, "tiny", CELLS | T, nwalkers=6, nmoves=400, dense=0.35, squash=shear, dr_max=0.5,
+                         dshear=0.3, dstretch=0.1, min_ar=0.05, min_ang=3.0)
+    assert 0 < dec["accepted"].mean() < 1
+    props, dec = _replay(eng, oracle, "tiny1", CELLS | T, nwalkers=6, nmoves=400, dense=0.45, squash=shear, dr_max=0.5,
+                         dshear=0.3, dstretch=0.1, min_ar=0.05, min_ang=3.0)
+    assert 0 < dec["accepted"].mean() < 1
+
+
+def test_cells_propose_mode(eng, oracle):
+    _replay(eng, oracle, "C1", CELLS | 32, nwalkers=6, nmoves=60, mode=1)
+    _replay(eng, oracle, "C4s", CELLS | 128, nwalkers=4, nmoves=60, mode=1, dense=0.4)
+
+
+@pytest.mark.parametrize("shape,T,sweeps,density", [("C1", 0, 5, None), ("C2", 0, 8, 0.6), ("C4s", 128, 3, 0.4), ("C4", 0, 1, None),
+                                                    ("C4", 128, 1, 0.5), ("C5", 0, 1, None), ("C5", 128, 1, 0.45),
+                                                    ("C5", 256, 1, 0.45), ("d140", 0, 2, 0.3), ("h15", 64, 5, 0.25)])
+def test_cells_mc_run_trajectory_bit_exact(eng, oracle, shape, T, sweeps, density):
+    """Self-driving walks with the cell list for every walker, up to the full C4 / C5 walkers, dilute and dense."""
+    nw = 8 if shape not in ("C4", "C5") else 5
+    cfg, H, R, k = make_walkers(shape, nw, seed=33)
+    if density:
+        H, R = compress(cfg, H, R, density, 33)
+    seed = 515151
+    limit = float(np.median([oracle.volume(H[w]) for w in range(nw)]))
+    pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=CELLS | T)
+    ids = [3, 0, 4, 1]
+    att, acc = pool.mc_run(sweeps, ids=ids, volume_limit=limit)
+    ctrs = np.zeros(nw, dtype=np.uint64)
+    o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, ids, sweeps, limit, seed, np.array(ids), ctrs)
+    assert np.array_equal(att.cpu().numpy().astype(np.uint64), o_att)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+    assert_state_equal(pool, H, R)
+    assert np.array_equal(pool.vol.cpu().numpy()[ids], o_vol)
+    assert not pool.check_overlap().cpu().numpy().any()
+
+
+@pytest.mark.parametrize("shape", ["C4", "C5", "d140", "p7x"])
+def test_default_dispatch_shares_a_walk_between_kernels(eng, oracle, shape):
+    """threads_per_walker = 0 on large chain systems: the dilute walkers of the batch are walked by the warp-per-move
+    kernel, the dense ones by the cell-list kernel (two launches, each skipping the other's walkers) -- every walker is
+    walked exactly once and the result is the oracle's."""
+    if shape == "p7x":
+        SHAPES["p7x"] = (40, 7, [2, 20, 20, 10, 3, 3])   # 280 beads on the cooperative kernel: cell list per walker (mode 2)
+    nw = 6
+    cfg, H, R, k = make_walkers(shape, nw, seed=35)
+    dense_H, dense_R = compress(cfg, H[:3].copy(), R[:3].copy(), 0.5 if shape != "d140" else 0.4, 35)
+    H[:3], R[:3] = dense_H, dense_R          # walkers 0-2 dense (rho >= 0.4), 3-5 dilute (rho = 1/15)
+    N = R.shape[1]
+    rho = np.array([N / oracle.volume(H[w]) for w in range(nw)])
+    assert (rho[:3] > 0.35).all() and (rho[3:] < 0.1).all()
+    seed = 99
+    pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=0)
+    limit = 1e300
+    for sweeps in (1, 1):
+        att, acc = pool.mc_run(sweeps, volume_limit=limit)
+        ctrs_before = pool.ctr.cpu().numpy().copy()
+    ctrs = np.zeros(nw, dtype=np.uint64)
+    for sweeps in (1, 1):
+        o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, np.arange(nw), sweeps, limit, seed, np.arange(nw), ctrs)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+    assert_state_equal(pool, H, R)
+    assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
+    if shape == "p7x":
+        del SHAPES["p7x"]
