@@ -387,11 +387,12 @@ static int check_cfg(const hans_cfg *c)
     return HANS_OK;
 }
 
-static size_t cta_smem_bytes(const hans_cfg *c, int T, bool cells = false)
+static size_t cta_smem_bytes(const hans_cfg *c, int T, int cells_mode = 0)
 {
     const int gpc = (T == 32) ? 4 : 1;
     const int N = c->nchains * c->nbeads;
-    return (walker_smem_bytes(N, c->nbeads, T) + (cells ? cell_smem_bytes(N) : 0)) * gpc + cta_extra_bytes(c->nbeads, c->nexclude);
+    return (walker_smem_bytes(N, c->nbeads, T) + (cells_mode ? cell_smem_bytes(N, cells_mode == 2) : 0)) * gpc +
+           cta_extra_bytes(c->nbeads, c->nexclude);
 }
 
 static int sm_count()
@@ -422,6 +423,7 @@ static int grid_for(int n, int T)
 
 static int pick_T(const hans_cfg *c, int T)
 {
+    T &= ~HANS_TPW_CELLS; // (the flag only steers the walk kernels)
     if (T >= 0 && T < 32) T = hans_default_threads_per_walker(c); // 1..31 only steer the walk kernels
     if (T != 32 && T != 64 && T != 128 && T != 256) return -1;
     return T;
@@ -485,10 +487,10 @@ static int pick_W(const hans_cfg *c, int tpw)
 
 // One CTA of NWARP warps per walker, one warp per move of a speculative window (hans_team.cuh): chains only
 // (the pruning works on chain bounding spheres), and the walker plus NWARP trial chains must fit shared memory.
-static size_t team_smem_bytes(const hans_cfg *c, int nwarp)
+static size_t team_smem_bytes(const hans_cfg *c, int nwarp, bool box_cells = false)
 {
     return walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp) +
-           team_tail_bytes(nwarp) + cta_extra_bytes(c->nbeads, c->nexclude);
+           team_tail_bytes(nwarp) + (box_cells ? cell_smem_bytes(c->nchains * c->nbeads, true) : 0) + cta_extra_bytes(c->nbeads, c->nexclude);
 }
 static bool team_applies(const hans_cfg *c, int nwarp)
 {
@@ -499,7 +501,8 @@ template <bool REPLAY> static int launch_team(WalkArgs a, int nwarp, cudaStream_
 {
     const hans_cfg *c = &a.cfg;
     a.team_res = (int)((walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp)) / 4);
-    const size_t smem = team_smem_bytes(c, nwarp);
+    if (a.cells_mode == 2 && team_smem_bytes(c, nwarp, true) > 227 * 1024) a.cells_mode = 0;
+    const size_t smem = team_smem_bytes(c, nwarp, a.cells_mode == 2);
     const int cap = sm_count() * 8, grid = a.n_active < cap ? a.n_active : cap;
     int rc = HANS_OK;
 #define TEAM_LAUNCH(NN, WW)                                                        \
@@ -586,14 +589,15 @@ int hans_default_team(const hans_cfg *cfg)
     return 0;
 }
 
-// Bead number density above which the cell-list kernel takes a walker over from the sphere-pruning kernels when
-// threads_per_walker = 0 (measured crossover, profiles/r02_cells_*; HANS_RHO_SPLIT overrides it for measurements)
+// Bead number density of a trial configuration above which a box move is tested through the cell list instead of the
+// chain-pair pass when threads_per_walker = 0 (measured crossover, profiles/r02_cells_*; HANS_RHO_SPLIT overrides it for
+// measurements, 0 switches the cell list off)
 static double rho_split()
 {
     static double v = -1.0;
     if (v < 0.0) {
         const char *e = getenv("HANS_RHO_SPLIT");
-        v = e ? atof(e) : 0.30;
+        v = e ? atof(e) : 0.35;
     }
     return v;
 }
@@ -612,7 +616,7 @@ static int cells_T(const hans_cfg *c)
 static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory, int T, cudaStream_t st)
 {
     int rc = HANS_OK;
-    const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode != 0);
+    const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode);
     if (from_memory) {
         DISPATCH_T(T, {
             rc = prep_kernel(walk_kernel<TT, true>, smem);
@@ -631,7 +635,7 @@ static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory,
 }
 
 // does the cell-list kernel fit shared memory for this shape (with T threads per walker)?
-static bool cells_fit(const hans_cfg *cfg, int T) { return cta_smem_bytes(cfg, T, true) <= 227 * 1024; }
+static bool cells_fit(const hans_cfg *cfg, int T, int mode = 1) { return cta_smem_bytes(cfg, T, mode) <= 227 * 1024; }
 
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
 {
@@ -651,21 +655,11 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         const int nwarp = threads_per_walker - 20;
         if (!team_applies(cfg, nwarp))
             return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
-        if (dflt && cells_fit(cfg, cells_T(cfg)) && rho_split() > 0.0) {
-            // default for large chain systems: two launches share the walk -- the warp-per-move kernel takes the walkers
-            // below the density split, the cell-list kernel the dense ones (where bounding spheres prune nothing)
-            WalkArgs lo = a, hi = a;
-            unsigned char *flags = nullptr;
-            CK(cudaMallocAsync((void **)&flags, (size_t)a.n_active, st));
-            classify_kernel<<<(a.n_active + 127) / 128, 128, 0, st>>>(a.H, a.ids, a.n_active, cfg->nchains * cfg->nbeads, rho_split(), flags);
-            lo.gate = 1; hi.gate = 2;
-            lo.gate_flags = hi.gate_flags = flags;
-            lo.rho_split = hi.rho_split = rho_split();
-            hi.cells_mode = 1;
-            int rc = from_memory ? launch_team<true>(lo, nwarp, st) : launch_team<false>(lo, nwarp, st);
-            if (rc == HANS_OK) rc = launch_coop(cfg, hi, from_memory, cells_T(cfg), st);
-            cudaFreeAsync(flags, st);
-            return rc;
+        if (dflt && rho_split() > 0.0 && cfg->nchains * cfg->nbeads >= 192) {
+            // default for large chain systems: box moves of DENSE trial configurations (where bounding spheres prune nothing
+            // and the chain-pair pass degenerates to all pairs) go through a cell list of the trial configuration
+            a.cells_mode = 2;
+            a.rho_split = rho_split();
         }
         return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
     }
@@ -677,8 +671,8 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
     }
     const int T = pick_T(cfg, threads_per_walker);
     if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 24, 28, 32, 64, 128 or 256 (optionally | HANS_TPW_CELLS)");
-    if (dflt && cfg->nchains * cfg->nbeads >= 192 && cells_fit(cfg, T) && rho_split() > 0.0) {
-        a.cells_mode = 2; // shapes that run on this kernel by default: the cell list per walker, above the density split
+    if (dflt && cfg->nchains * cfg->nbeads >= 192 && cells_fit(cfg, T, 2) && rho_split() > 0.0) {
+        a.cells_mode = 2; // box moves of dense trial configurations through the cell list
         a.rho_split = rho_split();
     }
     return launch_coop(cfg, a, from_memory, T, st);

@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(32, HANS_LEAN_MIN_CTAS) walk_lean_kernel(const
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     for (int k = blockIdx.x; k < a.n_active; k += gridDim.x) {
         const int wi = a.ids ? a.ids[k] : k;
-        if (gate_skips(a, k)) continue;
         load_walker<T>(w, a.H, a.R, wi, true);
         CellRegs cr = load_cell_regs(w);
         const unsigned sb = shared_base();

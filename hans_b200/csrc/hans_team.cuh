@@ -215,7 +215,10 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
 {
     constexpr int T = 32 * NWARP;
     static_assert(NWARP >= 2 && NWARP <= 8, "result words carry 8 bits per earlier move");
-    const WCtx w = setup_ctx_g<T, 1>(a.cfg, NWARP, team_tail_bytes(NWARP));
+    WCtx w = setup_ctx_g<T, 1>(a.cfg, NWARP, team_tail_bytes(NWARP) + (a.cells_mode == 2 ? (int)cell_smem_bytes(a.cfg.nchains * a.cfg.nbeads, true) : 0),
+                               team_tail_bytes(NWARP));
+    w.cells = a.cells_mode == 2 ? 2 : 0; // box moves through a cell list of the trial configuration when it is dense
+    w.rho_box = (float)a.rho_split;
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const int nb = NB ? NB : w.nb;
     unsigned *res = reinterpret_cast<unsigned *>(smem) + a.team_res; // (walker + window area) / 4, from the launcher
@@ -226,7 +229,6 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     for (int k = blockIdx.x; k < a.n_active; k += gridDim.x) {
         const int wi = a.ids ? a.ids[k] : k;
-        if (gate_skips(a, k)) continue; // (uniform over the CTA)
         load_walker<T>(w, a.H, a.R, wi, true);
         Filt f = load_filt(W_SF(w));
         const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];

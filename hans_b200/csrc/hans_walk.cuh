@@ -68,7 +68,10 @@ struct WCtx {
     int rad;  // float index of the chain bounding radii RAD[nc]
     int lst;  // int index of the near list LST[T] (+ its counter at lst - 1 ... see near_list())
     int cl;   // int index of the per-walker cell list area (cell_smem_bytes), behind the window area / tail
-    int cells; // != 0: overlap tests go through the cell list (set per walker by the kernels that carry the area)
+    int cells; // bit 0: every overlap test goes through the per-walker cell list, which the chain moves keep up to date;
+               // bit 1: only box moves do (a list of the trial configuration, built per move), and only when the trial
+               // configuration is denser than rho_box.  Set per walker by the kernels that carry the area.
+    float rho_box;
     unsigned nbmagic, ncmagic; // x / nb = umulhi(x, nbmagic), x / nc = umulhi(x, ncmagic) for x < 2^16
 };
 #define W_P(w) ((w).D0)
@@ -122,21 +125,27 @@ __host__ __device__ inline size_t window_smem_bytes(int nb, int W)
 // Per-walker cell list (the role of hs_alkane's link cells, which the reference bypasses at MCNS.py:603): bins in
 // FRACTIONAL space, n_k = floor(w_k / 1.001) per axis (w_k = perpendicular width of the cell along axis k), capped at
 // CL_M per axis.  Layout (ints): dims[8] = {n0, n1, n2, nbins} of the current cell and of the trial cell of a box
-// move; head[CL_CAP], head2[CL_CAP] (first bead of each bin, -1 = empty); next[N], next2[N] (singly linked).
+// move; head2[CL_CAP], next2[N]: the list of the TRIAL configuration of a box move (first bead of each bin, -1 = empty;
+// singly linked); head[CL_CAP], next[N]: the list of the current configuration, kept up to date by the chain moves.
+// A kernel that uses the list only for box moves (mode 2) allocates the area without the last two arrays.
 constexpr int CL_M = 10;
 constexpr int CL_CAP = CL_M * CL_M * CL_M;
-__host__ __device__ inline size_t cell_smem_bytes(int N) { return (4 * ((size_t)8 + 2 * CL_CAP + 2 * (size_t)N) + 63) & ~(size_t)63; }
+__host__ __device__ inline size_t cell_smem_bytes(int N, bool box_only = false)
+{
+    return (4 * ((size_t)8 + (box_only ? 1 : 2) * (CL_CAP + (size_t)N)) + 63) & ~(size_t)63;
+}
 #define CL_DIMS(w) ((w).cl)
-#define CL_HEAD(w) ((w).cl + 8)
-#define CL_HEAD2(w) ((w).cl + 8 + CL_CAP)
-#define CL_NEXT(w) ((w).cl + 8 + 2 * CL_CAP)
-#define CL_NEXT2(w) ((w).cl + 8 + 2 * CL_CAP + (w).N)
+#define CL_HEAD2(w) ((w).cl + 8)
+#define CL_NEXT2(w) ((w).cl + 8 + CL_CAP)
+#define CL_HEAD(w) ((w).cl + 8 + CL_CAP + (w).N)
+#define CL_NEXT(w) ((w).cl + 8 + 2 * CL_CAP + (w).N)
 #define SMI (reinterpret_cast<int *>(smem))
 
 // GPC walker groups of T threads per CTA; W > 0 adds the window area behind each walker's ring, `tail` bytes
-// (a multiple of 64) behind that (the warp-per-move kernel's scratch, or the cell list of walk_kernel)
+// (a multiple of 64) behind that (the warp-per-move kernel's scratch and / or the cell list, which starts cl_off bytes
+// into the tail)
 template <int T, int GPC>
-__device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail = 0)
+__device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail = 0, int cl_off = 0)
 {
     WCtx w;
     w.nb = c.nbeads; w.nc = c.nchains; w.N = c.nbeads * c.nchains; w.nex = c.nexclude;
@@ -159,8 +168,9 @@ __device__ __forceinline__ WCtx setup_ctx_g(const hans_cfg &c, int W, int tail =
     w.ncmagic = 0xFFFFFFFFu / (unsigned)w.nc + 1u;
     w.wc = (base + core) / 8;
     w.w4 = (base + core + 24 * W * w.nb + 15) / 16;
-    w.cl = (base + core + (int)window_smem_bytes(w.nb, W)) / 4;
+    w.cl = (base + core + (int)window_smem_bytes(w.nb, W) + cl_off) / 4;
     w.cells = 0;
+    w.rho_box = 0.0f;
     const int extra = per * GPC;
     w.cfg = extra / 8;
     w.itab = (extra + (int)((sizeof(hans_cfg) + 15) & ~(size_t)15)) / 2;
@@ -544,25 +554,37 @@ __device__ __noinline__ void cl_build(WCtx w, int hi, int q4, int dims, int head
     gsync<T>();
 }
 
-// the chain's beads [b0, nb) leave the bins of their old shadows (F4) and enter those of the trial shadows (C4);
-// one thread: concurrent unlinking is not safe, and a chain is a handful of beads.  Call BEFORE F4 is overwritten.
-__device__ __noinline__ void cl_move_chain(WCtx w, int ichain, int b0)
+// the chain's beads leave the bins of their old shadows (F4) and enter those of the trial shadows (C4) -- ALL of them:
+// a dihedral move with a flip relabels the beads it does not move.  Called by ONE WARP (all 32 lanes): the bins are
+// computed in parallel, then lane 0 relinks the beads whose bin changed one after the other (concurrent unlinking is
+// not safe; in the dense regime most beads stay in their bin).  Call BEFORE F4 is overwritten.
+__device__ __noinline__ void cl_move_chain(WCtx w, int ichain)
 {
     const Grid g = load_grid(CL_DIMS(w));
-    const int head = CL_HEAD(w), next = CL_NEXT(w), c0 = ichain * w.nb;
+    const int head = CL_HEAD(w), next = CL_NEXT(w), c0 = ichain * w.nb, ln = threadIdx.x & 31;
 #pragma unroll 1
-    for (int b = b0; b < w.nb; ++b) {
-        const int i = c0 + b;
-        const int bo = cl_bin(g, SM4[W_F4(w) + i]), bn = cl_bin(g, SM4[W_C4(w) + b]);
-        if (bo == bn) continue;
-        int j = SMI[head + bo], prev = -1;
-        while (j != i && j >= 0) { prev = j; j = SMI[next + j]; }
-        if (j == i) {
-            if (prev < 0) SMI[head + bo] = SMI[next + i]; else SMI[next + prev] = SMI[next + i];
+    for (int p0 = 0; p0 < w.nb; p0 += 32) {
+        const int b = p0 + ln;
+        int bo = 0, bn = 0;
+        if (b < w.nb) { bo = cl_bin(g, SM4[W_F4(w) + c0 + b]); bn = cl_bin(g, SM4[W_C4(w) + b]); }
+        unsigned mask = __ballot_sync(FULL, bo != bn);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const int fo = __shfl_sync(FULL, bo, l), tn = __shfl_sync(FULL, bn, l);
+            if (ln == 0) {
+                const int i = c0 + p0 + l;
+                int j = SMI[head + fo], prev = -1;
+                for (int guard = 0; j != i && j >= 0 && guard < w.N; ++guard) { prev = j; j = SMI[next + j]; }
+                if (j == i) {
+                    if (prev < 0) SMI[head + fo] = SMI[next + i]; else SMI[next + prev] = SMI[next + i];
+                }
+                SMI[next + i] = SMI[head + tn];
+                SMI[head + tn] = i;
+            }
         }
-        SMI[next + i] = SMI[head + bn];
-        SMI[head + bn] = i;
     }
+    __syncwarp();
 }
 
 // Does the trial chain (CN / C4, bounding radius Rt) overlap anything?  NB > 0: beads per chain known
@@ -683,15 +705,15 @@ __device__ __forceinline__ bool chain_overlaps_pruned(const WCtx &w, const Filt 
 
 // Does the trial chain (CN / C4) overlap anything?  Cell-list version: one task per (moved trial bead, neighbour bin),
 // spread over the group's threads; every bead found there that belongs to another chain goes through the float32
-// filter.  Same votes and the same float64 settle as chain_overlaps_pruned.
-template <int T>
-__device__ __forceinline__ bool chain_overlaps_cells(const WCtx &w, const Filt &f, int ichain, int b0, bool intra, unsigned &pairs)
+// filter.  Same votes and the same float64 settle as chain_overlaps_pruned.  G3: at least three bins along every axis
+// (27 distinct neighbours; the task index is decoded with compile-time divisions).
+template <int T, bool G3>
+__device__ __forceinline__ void chain_cells_scan(const WCtx &w, const Filt &f, const Grid &g, int ichain, int b0, bool &ov, bool &amb,
+                                                 unsigned &pairs)
 {
-    const Grid g = load_grid(CL_DIMS(w));
     const int nb = w.nb, c0 = ichain * nb, f4 = W_F4(w), c4 = W_C4(w), head = CL_HEAD(w), next = CL_NEXT(w);
-    const int k0 = g.n0 < 3 ? g.n0 : 3, k1 = g.n1 < 3 ? g.n1 : 3, k2 = g.n2 < 3 ? g.n2 : 3;
+    const int k0 = G3 ? 3 : (g.n0 < 3 ? g.n0 : 3), k1 = G3 ? 3 : (g.n1 < 3 ? g.n1 : 3), k2 = G3 ? 3 : (g.n2 < 3 ? g.n2 : 3);
     const int k12 = k1 * k2, K = k0 * k12, ntask = (nb - b0) * K;
-    bool ov = false, amb = false;
 #pragma unroll 1
     for (int t = w.lane; t < ntask; t += T) {
         const int bi = t / K, o = t - bi * K;
@@ -700,7 +722,7 @@ __device__ __forceinline__ bool chain_overlaps_cells(const WCtx &w, const Filt &
         const int bin = (cl_nbr(cl_coord(tb.x, g.n0), o0, g.n0) * g.n1 + cl_nbr(cl_coord(tb.y, g.n1), o1, g.n1)) * g.n2 +
                         cl_nbr(cl_coord(tb.z, g.n2), o2, g.n2);
 #pragma unroll 1
-        for (int j = SMI[head + bin]; j >= 0; j = SMI[next + j]) {
+        for (int j = SMI[head + bin], guard = 0; j >= 0 && guard < w.N; j = SMI[next + j], ++guard) {
             if ((unsigned)(j - c0) < (unsigned)nb) continue;
             const float4 sj = SM4[f4 + j];
             const float r2 = r2_f32(f, sj.x - tb.x, sj.y - tb.y, sj.z - tb.z);
@@ -709,6 +731,16 @@ __device__ __forceinline__ bool chain_overlaps_cells(const WCtx &w, const Filt &
             pairs += 1u;
         }
     }
+}
+
+template <int T>
+__device__ __forceinline__ bool chain_overlaps_cells(const WCtx &w, const Filt &f, int ichain, int b0, bool intra, unsigned &pairs)
+{
+    const Grid g = load_grid(CL_DIMS(w));
+    const int c4 = W_C4(w);
+    bool ov = false, amb = false;
+    if (g.n0 >= 3 && g.n1 >= 3 && g.n2 >= 3) chain_cells_scan<T, true>(w, f, g, ichain, b0, ov, amb, pairs);
+    else chain_cells_scan<T, false>(w, f, g, ichain, b0, ov, amb, pairs);
     bool amb_intra = false;
     if (intra) {
         const uchar2 *tab = W_ITAB(w);
@@ -756,7 +788,7 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
     bool ov;
     float Rt = 0.0f;
     if (nb > 1) Rt = intra ? chain_radius(cn, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
-    if (w.cells) {
+    if (w.cells & 1) {
         ov = chain_overlaps_cells<T>(w, load_filt(W_SF(w)), ichain, b0, intra, pairs);
     } else if (nb > 1) {
         ov = chain_overlaps_pruned<T, 0>(w, load_filt(W_SF(w)), ichain, b0, intra, Rt, pairs);
@@ -765,8 +797,8 @@ __device__ __forceinline__ Dec move_chain(const WCtx &w, const PropRec *p, int m
     }
     const double boltz = ov ? 0.0 : 1.0;
     if ((mode == HANS_MODE_PROPOSE) || (p->u_acc < boltz)) { // MCNS.py:372
-        if (w.cells) { // (every thread is past its reads of the list: the vote above was a group barrier)
-            if (w.lane == 0) cl_move_chain(w, ichain, b0);
+        if (w.cells & 1) { // (every thread is past its reads of the list: the vote above was a group barrier)
+            if (w.lane < 32) cl_move_chain(w, ichain);
             gsync<T>();
         }
         const int f4 = W_F4(w) + c0;
@@ -835,38 +867,37 @@ __device__ __noinline__ bool trial_overlap_exact(WCtx w, bool with_intra)
 }
 
 // All pairs of the TRIAL beads (TP / G4 under the trial cell) through a cell list built for the trial cell: one task
-// per (bead i, neighbour bin), pairs (i, j > i) only so that every pair is tested once; same-chain pairs only if
-// with_intra and further apart than nexclude.  A vote every CL_VOTE tasks per thread ends a rejected move early.
-// Pairs inside the filter's band: the first one per thread is settled in float64, more than one -> the full float64 pass.
+// per (bead i, neighbour bin).  G3 (at least three bins along every axis): the bead's own bin (pairs j > i) and the 13
+// "forward" neighbours, so every pair of beads meets once; otherwise every distinct neighbour bin with j > i.  Same-chain
+// pairs only if with_intra and further apart than nexclude.  A vote every CL_VOTE tasks per thread ends a rejected move
+// early.  Pairs inside the filter's band: the first one per thread is settled in float64, more than one -> the full pass.
 #define CL_VOTE 8
-template <int T>
-__device__ __forceinline__ bool trial_overlap_cells(const WCtx &w, bool with_intra, unsigned &pairs)
+template <int T, bool G3>
+__device__ __forceinline__ bool trial_cells_scan(const WCtx &w, const Filt &f, const Grid &g, bool with_intra, bool &ov, int &namb,
+                                                 int &ai, int &aj, unsigned &pairs)
 {
-    cl_build<T>(w, W_SH(w) + 27, W_G4(w), CL_DIMS(w) + 4, CL_HEAD2(w), CL_NEXT2(w));
-    const Filt f = load_filt(W_SF(w) + SF_TRIAL);
-    const Grid g = load_grid(CL_DIMS(w) + 4);
-    const int nb = w.nb, N = w.N, g4 = W_G4(w), tp = W_TP(w), sh = W_SH(w) + 18, head = CL_HEAD2(w), next = CL_NEXT2(w);
-    const int k0 = g.n0 < 3 ? g.n0 : 3, k1 = g.n1 < 3 ? g.n1 : 3, k2 = g.n2 < 3 ? g.n2 : 3;
-    const int k12 = k1 * k2, K = k0 * k12, ntask = N * K;
+    const int nb = w.nb, N = w.N, g4 = W_G4(w), head = CL_HEAD2(w), next = CL_NEXT2(w);
+    const int k0 = G3 ? 3 : (g.n0 < 3 ? g.n0 : 3), k1 = G3 ? 3 : (g.n1 < 3 ? g.n1 : 3), k2 = G3 ? 3 : (g.n2 < 3 ? g.n2 : 3);
+    const int k12 = k1 * k2, K = G3 ? 14 : k0 * k12, ntask = N * K;
     const int nex_eff = with_intra ? w.nex : 0x3fffffff;
-    bool ov = false;
-    int namb = 0, ai = 0, aj = 0;
 #pragma unroll 1
     for (int t0 = 0; t0 < ntask; t0 += T * CL_VOTE) {
 #pragma unroll 1
         for (int u = 0; u < CL_VOTE; ++u) {
             const int t = t0 + u * T + w.lane;
             if (t < ntask) {
-                const int i = t / K, o = t - i * K;
+                const int i = t / K, oo = t - i * K;
+                const int o = G3 ? oo + 13 : oo; // G3: linear offsets 13 (own bin) .. 26 of the 27
                 const int o0 = o / k12, o1 = (o - o0 * k12) / k2, o2 = o - o0 * k12 - o1 * k2;
                 const float4 si = SM4[g4 + i];
                 const int bin = (cl_nbr(cl_coord(si.x, g.n0), o0, g.n0) * g.n1 + cl_nbr(cl_coord(si.y, g.n1), o1, g.n1)) * g.n2 +
                                 cl_nbr(cl_coord(si.z, g.n2), o2, g.n2);
                 const int ci0 = div_nb(w, i) * nb;
+                const bool ordered = !G3 || oo == 0; // the same bin on both sides: take each pair once
 #pragma unroll 1
-                for (int j = SMI[head + bin]; j >= 0; j = SMI[next + j]) {
-                    if (j <= i) continue;
-                    if ((unsigned)(j - ci0) < (unsigned)nb && (j - i) <= nex_eff) continue; // same chain, excluded
+                for (int j = SMI[head + bin], guard = 0; j >= 0 && guard < N; j = SMI[next + j], ++guard) {
+                    if (ordered && j <= i) continue;
+                    if ((unsigned)(j - ci0) < (unsigned)nb && (j > i ? j - i : i - j) <= nex_eff) continue; // same chain, excluded
                     const float4 sj = SM4[g4 + j];
                     const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
                     ov |= (r2 < f.lo);
@@ -880,6 +911,69 @@ __device__ __forceinline__ bool trial_overlap_cells(const WCtx &w, bool with_int
         }
         if (gany<T>(ov)) return true;
     }
+    return false;
+}
+
+// The same scan for grids of at least three bins per axis, sixteen lanes per bead: lane s of a group owns ONE of the 14
+// forward offsets (s = 0: the bead's own bin) for the whole scan, so no task index is decoded inside the loop.
+template <int T>
+__device__ __forceinline__ bool trial_cells_scan16(const WCtx &w, const Filt &f, const Grid &g, bool with_intra, bool &ov, int &namb,
+                                                   int &ai, int &aj, unsigned &pairs)
+{
+    const int nb = w.nb, N = w.N, g4 = W_G4(w), head = CL_HEAD2(w), next = CL_NEXT2(w);
+    const int sub = w.lane & 15, grp = w.lane >> 4;
+    constexpr int BPP = T / 16; // beads per pass of the group
+    const int o = sub + 13;     // linear offsets 13 (own bin) .. 26 of the 27
+    const int d0 = o / 9 - 1, d1 = (o - (o / 9) * 9) / 3 - 1, d2 = o % 3 - 1;
+    const bool act = sub < 14, ordered = sub == 0;
+    const int nex_eff = with_intra ? w.nex : 0x3fffffff;
+#pragma unroll 1
+    for (int i0 = 0; i0 < N; i0 += BPP * CL_VOTE) {
+#pragma unroll 1
+        for (int u = 0; u < CL_VOTE; ++u) {
+            const int i = i0 + u * BPP + grp;
+            if (act && i < N) {
+                const float4 si = SM4[g4 + i];
+                int bx = cl_coord(si.x, g.n0) + d0, by = cl_coord(si.y, g.n1) + d1, bz = cl_coord(si.z, g.n2) + d2;
+                bx = bx < 0 ? bx + g.n0 : (bx >= g.n0 ? bx - g.n0 : bx);
+                by = by < 0 ? by + g.n1 : (by >= g.n1 ? by - g.n1 : by);
+                bz = bz < 0 ? bz + g.n2 : (bz >= g.n2 ? bz - g.n2 : bz);
+                int j = SMI[head + (bx * g.n1 + by) * g.n2 + bz];
+                if (j >= 0) {
+                    const int ci0 = div_nb(w, i) * nb;
+#pragma unroll 1
+                    for (int guard = 0; j >= 0 && guard < N; j = SMI[next + j], ++guard) {
+                        if (ordered && j <= i) continue;
+                        if ((unsigned)(j - ci0) < (unsigned)nb && (j > i ? j - i : i - j) <= nex_eff) continue; // same chain, excluded
+                        const float4 sj = SM4[g4 + j];
+                        const float r2 = r2_f32(f, sj.x - si.x, sj.y - si.y, sj.z - si.z);
+                        ov |= (r2 < f.lo);
+                        if (!(r2 < f.lo) && !(r2 > f.hi)) {
+                            if (namb == 0) { ai = i; aj = j; }
+                            ++namb;
+                        }
+                        pairs += 1u;
+                    }
+                }
+            }
+        }
+        if (gany<T>(ov)) return true;
+    }
+    return false;
+}
+
+template <int T>
+__device__ __forceinline__ bool trial_overlap_cells(const WCtx &w, bool with_intra, unsigned &pairs)
+{
+    cl_build<T>(w, W_SH(w) + 27, W_G4(w), CL_DIMS(w) + 4, CL_HEAD2(w), CL_NEXT2(w));
+    const Filt f = load_filt(W_SF(w) + SF_TRIAL);
+    const Grid g = load_grid(CL_DIMS(w) + 4);
+    const int tp = W_TP(w), sh = W_SH(w) + 18;
+    bool ov = false;
+    int namb = 0, ai = 0, aj = 0;
+    const bool hit = (g.n0 >= 3 && g.n1 >= 3 && g.n2 >= 3) ? trial_cells_scan16<T>(w, f, g, with_intra, ov, namb, ai, aj, pairs)
+                                                           : trial_cells_scan<T, false>(w, f, g, with_intra, ov, namb, ai, aj, pairs);
+    if (hit) return true;
     if (gany<T>(namb > 0)) {
         if (namb > 0)
             ov |= pair_r2(smem + sh, smem + sh + 9, smem[tp + 3 * aj] - smem[tp + 3 * ai], smem[tp + 3 * aj + 1] - smem[tp + 3 * ai + 1],
@@ -1000,10 +1094,10 @@ __device__ __forceinline__ bool trial_overlap_pruned(const WCtx &w, bool with_in
 // loop (8 independent pair tests per lane between votes); pairs inside the band are settled by
 // one float64 pass afterwards, and only if nothing overlapped for certain.
 template <int T>
-__device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, unsigned &pairs)
+__device__ __forceinline__ bool trial_overlap(const WCtx &w, bool with_intra, bool use_cells, unsigned &pairs)
 {
     if (w.nc == 1) return trial_overlap_exact<T>(w, with_intra);
-    if (w.cells) return trial_overlap_cells<T>(w, with_intra, pairs);
+    if (use_cells) return trial_overlap_cells<T>(w, with_intra, pairs);
     if (w.nb > 1) return trial_overlap_pruned<T>(w, with_intra, pairs);
     const Filt f = load_filt(W_SF(w) + SF_TRIAL);
     const int nb = w.nb, N = w.N, half = N >> 1, g4 = W_G4(w);
@@ -1189,10 +1283,19 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         if (aspect_fails(Hn, c->min_ar)) reason = HANS_REJ_ASPECT;                // MCNS.py:194,243
         else if (angle_fails(Hn, c->cos_min_ang)) reason = HANS_REJ_ANGLE;        // MCNS.py:196,245
     }
-    if (reason == HANS_ACCEPT && trial_overlap<T>(w, !is_vol, out.pairs)) reason = HANS_REJ_OVERLAP; // MCNS.py:198,247
+    // the cell list serves the box move when it is maintained anyway, or (bit 1) when bounding spheres prune nothing: the
+    // typical reach of a pair of chains (two bounding radii of a zig-zag chain + sigma) exceeds half the smallest
+    // perpendicular width of the trial cell, so the chain-pair pass would test all bead pairs -- and the trial configuration
+    // is dense enough for the list to pay (measured crossover, profiles/r02_cells_probe.md)
+    bool use_cells = (w.cells & 1) != 0;
+    if (!use_cells && (w.cells & 2)) {
+        const float reach = 2.0f * 0.82f * (float)c->bondlength * (float)(w.nb >> 1) + 1.0f;
+        use_cells = !(reach < SMF[W_SF(w) + SF_TRIAL + 8]) && !((float)((double)w.N / fabs(det3(Hn))) < w.rho_box);
+    }
+    if (reason == HANS_ACCEPT && trial_overlap<T>(w, !is_vol, use_cells, out.pairs)) reason = HANS_REJ_OVERLAP; // MCNS.py:198,247
     if (mode == HANS_MODE_PROPOSE || reason == HANS_ACCEPT) {
         commit_trial<T>(w);
-        if (w.cells) {
+        if (w.cells & 1) {
             // (a shape rejection or a single-chain walker never built the trial list)
             if (reason == HANS_REJ_ASPECT || reason == HANS_REJ_ANGLE || w.nc == 1) cl_build<T>(w, sh + 9, W_F4(w), CL_DIMS(w), CL_HEAD(w), CL_NEXT(w));
             else cl_commit_trial<T>(w);
@@ -1214,7 +1317,7 @@ __device__ __noinline__ DecP move_box(WCtx w, int q, double volume_limit, int mo
         follow_cell<T>(w, W_TP(w), W_P(w), W_F4(w), sh + 27, sh, sh + 9);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
-        if (w.cells) cl_build<T>(w, sh + 9, W_F4(w), CL_DIMS(w), CL_HEAD(w), CL_NEXT(w)); // the shadows were recomputed
+        if (w.cells & 1) cl_build<T>(w, sh + 9, W_F4(w), CL_DIMS(w), CL_HEAD(w), CL_NEXT(w)); // the shadows were recomputed
     }
     out.accepted = reason == HANS_ACCEPT; out.reason = reason;
     out.boltz = reason == HANS_ACCEPT ? (is_vol ? boltz_f : 1.0) : 0.0;
@@ -1249,7 +1352,7 @@ __device__ __forceinline__ void load_walker(const WCtx &w, const double *gH, con
             for (int c = w.lane; c < w.nc; c += T) SMF[w.rad + c] = chain_radius(p + 3 * c * w.nb, w.nb);
         filter_params(sh, W_SF(w), w.lane == 0);
         gsync<T>();
-        if (w.cells) cl_build<T>(w, sh + 9, f4, CL_DIMS(w), CL_HEAD(w), CL_NEXT(w));
+        if (w.cells & 1) cl_build<T>(w, sh + 9, f4, CL_DIMS(w), CL_HEAD(w), CL_NEXT(w));
     }
 }
 
@@ -1287,55 +1390,26 @@ struct WalkArgs {
     int mode;
     int team_res; // warp-per-move kernel: int offset of its tail area in shared memory (set by the launcher)
     unsigned long long ctr_add; // proposals from memory: what the walk adds to the walkers' proposal counters
-    // Density gate: one walk may be served by two launches, each taking the walkers on its side of rho_split (bead
-    // number density N / V at the start of the walk, classified ONCE into gate_flags[k] by classify_kernel before the
-    // first of the two launches): 0 = every walker, 1 = only the dilute side (flag 0), 2 = only the dense side (flag 1).
-    // A skipped walker is not touched (state, counters, volume).
-    int gate;
-    const unsigned char *gate_flags;
-    // walk_kernel: 0 = no cell list, 1 = cell list for every walker, 2 = per walker, iff rho >= rho_split
+    // 0 = no cell list; 1 = the per-walker cell list serves every overlap test (walk_kernel only); 2 = only box moves
+    // whose trial configuration is denser than rho_split (walk_kernel and walk_team_kernel)
     int cells_mode;
     double rho_split;
 };
-
-__device__ __forceinline__ double walker_density(const WalkArgs &a, int wi, int N)
-{
-    double H[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) H[k] = a.H[(size_t)wi * 9 + k];
-    return (double)N / fabs(det3(H));
-}
-__device__ __forceinline__ bool gate_skips(const WalkArgs &a, int k)
-{
-    if (a.gate == 0) return false;
-    return (a.gate == 2) != (a.gate_flags[k] != 0);
-}
-
-// gate_flags[k] = walker ids[k] is on the dense side of the split
-__global__ void classify_kernel(const double *gH, const int32_t *ids, int n, int N, double rho_split, unsigned char *flags)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int wi = ids ? ids[k] : k;
-    double H[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) H[q] = gH[(size_t)wi * 9 + q];
-    flags[k] = !((double)N / fabs(det3(H)) < rho_split) ? 1 : 0;
-}
 
 template <int T, bool REPLAY>
 __global__ void __launch_bounds__(cta_threads<T>()) walk_kernel(const WalkArgs a)
 {
     constexpr int GPC = cta_threads<T>() / T;
-    WCtx w = setup_ctx<T>(a.cfg, a.cells_mode ? (int)cell_smem_bytes(a.cfg.nchains * a.cfg.nbeads) : 0);
+    WCtx w = setup_ctx<T>(a.cfg, a.cells_mode ? (int)cell_smem_bytes(a.cfg.nchains * a.cfg.nbeads, a.cells_mode == 2) : 0);
+    w.rho_box = (float)a.rho_split;
     const int g = threadIdx.x / T;
     const double limit = a.d_limit ? *a.d_limit : a.limit;
     const int mode = a.mode;
     for (int k0 = blockIdx.x * GPC; k0 < a.n_active; k0 += gridDim.x * GPC) {
         const int k = k0 + g;
-        if (k < a.n_active && !gate_skips(a, k)) {
+        if (k < a.n_active) {
             const int wi = a.ids ? a.ids[k] : k;
-            w.cells = a.cells_mode == 1 || (a.cells_mode == 2 && !(walker_density(a, wi, w.N) < a.rho_split));
+            w.cells = a.cells_mode; // 1: lists for every test; 2: box moves only, above rho_split
             load_walker<T>(w, a.H, a.R, wi, true);
             const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
             unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0}; // this lane's share

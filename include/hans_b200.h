@@ -59,8 +59,9 @@ enum {
 /* OR-ed into threads_per_walker (0, 32, 64, 128, 256): the cooperative kernel with the PER-WALKER CELL LIST -- bins in
  * fractional space at least 1.001 sigma wide in every direction, overlap candidates of a bead = the beads of the <= 27
  * bins around it (the role of hs_alkane's link cells, bypassed by the reference at MCNS.py:603).  Same decisions and
- * trajectories as every other kernel, bit for bit.  With threads_per_walker = 0 the library uses it by itself for
- * walkers whose bead number density N / V exceeds the measured crossover (dense regime: bounding spheres prune nothing). */
+ * trajectories as every other kernel, bit for bit.  With threads_per_walker = 0 the library uses a cell list of the TRIAL
+ * configuration by itself for the box moves of walkers of 192 beads and more once bounding spheres prune nothing (the
+ * reach of a pair of chains exceeds half the smallest cell width) and the bead density exceeds the measured crossover. */
 #define HANS_TPW_CELLS 4096
 
 /* Model + move parameters.  Replaces hs_alkane's module state set through
@@ -139,7 +140,7 @@ int hans_default_team(const hans_cfg *cfg);
  *                     any of 0, 32, 64, 128, 256 | HANS_TPW_CELLS: cooperative kernel with the per-walker cell list;
  *                     0 = the measured default per shape: hans_default_window if non-zero, else
  *                     hans_default_team if non-zero, else hans_default_threads_per_walker -- and, for walkers of 192
- *                     beads and more, the cell-list kernel for the walkers above the density crossover.
+ *                     beads and more, box moves of dense trial configurations through a cell list.
  *                     Every variant produces the same trajectory; the choice is speed only.
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,

@@ -1,8 +1,8 @@
 """The per-walker cell list (BASELINE.json north_star; the link cells the reference bypasses at
 /root/reference/NesSa/MCNS.py:603): decisions and trajectories must equal the all-pairs oracle's, bit for bit, in the
 dilute regime, in the dense regime (where bounding spheres prune nothing), in thin / sheared cells (axes with fewer than
-three bins), with explicit proposals and self-driving, and when a walk is SHARED between the warp-per-move kernel
-(dilute walkers) and the cell-list kernel (dense walkers) by the default dispatch."""
+three bins), with explicit proposals and self-driving, and in the default dispatch, where the warp-per-move and the
+cooperative kernel send only the box moves of dense trial configurations through a cell list."""
 import numpy as np
 import pytest
 
@@ -36,10 +36,42 @@ def assert_state_equal(pool, H, R):
     assert bad.size == 0, f"bead coordinates differ from oracle for walkers {bad[:8]}"
 
 
+def densify(eng, oracle, cfg, shape, H, R, k, density, seed, max_rounds=900, shrink=0.985):
+    """Walkers at a bead number density.  Small walkers: the oracle's own shrink / relax loop (tests/common.py).  Large
+    ones (hundreds of beads: minutes on the CPU): the same procedure on the device with the plain cooperative kernel
+    (threads_per_walker = 128, no cell list) -- only a way to MAKE dense start states; the comparison that follows is
+    against the oracle."""
+    N = R.shape[1]
+    if N < 200:
+        return compress(cfg, H, R, density, seed)
+    nchains, nbeads, mr = SHAPES[shape]
+    pool = make_pool(eng, shape, H, R, k, seed=seed + 1000, tpw=128)
+    relax = pool.cfg_with([0.0] + [float(x) for x in mr[1:4]] + [0.0, 0.0])
+    relax.dr_max, relax.dt_max, relax.dh_max = 0.3, 0.3, 0.3
+    nw = H.shape[0]
+    ids = torch.arange(nw, dtype=torch.int32, device=pool.device)
+    for _ in range(max_rounds):
+        todo = (N / pool.vol) < density
+        if not bool(todo.any()):
+            break
+        Hb, Rb = pool.H.clone(), pool.R.clone()
+        sel = ids[todo]
+        pool.change_box(sel, ((shrink - 1.0) * pool.H[todo]).cpu().numpy())
+        bad = pool.check_overlap().bool()
+        pool.H[bad] = Hb[bad]
+        pool.R[bad] = Rb[bad]
+        pool.refresh_volumes()
+        pool.mc_run(2, counters=False, cfg=relax, count_pairs=False)
+    H2, R2 = pool.get_state()
+    assert ((N / np.array([oracle.volume(h) for h in H2])) >= density * 0.98).all(), "could not reach the density"
+    assert not any(oracle.check_overlap(cfg, H2[w], R2[w]) for w in range(nw))
+    return H2, R2
+
+
 def _replay(eng, oracle, shape, tpw, nwalkers=8, nmoves=400, seed=21, dense=None, mode=0, squash=None, **kw):
     cfg, H, R, k = make_walkers(shape, nwalkers, seed=seed, **kw)
     if dense:
-        H, R = compress(cfg, H, R, dense, seed)
+        H, R = densify(eng, oracle, cfg, shape, H, R, k, dense, seed)
     if squash is not None:   # affine squash of cell and beads along one axis would overlap; shear instead (volume kept)
         for w in range(nwalkers):
             oracle.change_box(cfg, H[w], R[w], squash(w, H[w]))
@@ -107,14 +139,14 @@ def test_cells_propose_mode(eng, oracle):
 
 
 @pytest.mark.parametrize("shape,T,sweeps,density", [("C1", 0, 5, None), ("C2", 0, 8, 0.6), ("C4s", 128, 3, 0.4), ("C4", 0, 1, None),
-                                                    ("C4", 128, 1, 0.5), ("C5", 0, 1, None), ("C5", 128, 1, 0.45),
-                                                    ("C5", 256, 1, 0.45), ("d140", 0, 2, 0.3), ("h15", 64, 5, 0.25)])
+                                                    ("C4", 128, 1, 0.5), ("C5", 0, 1, None), ("C5", 128, 1, 0.3),
+                                                    ("C5", 256, 1, 0.3), ("d140", 0, 2, 0.25), ("h15", 64, 5, 0.25)])
 def test_cells_mc_run_trajectory_bit_exact(eng, oracle, shape, T, sweeps, density):
     """Self-driving walks with the cell list for every walker, up to the full C4 / C5 walkers, dilute and dense."""
     nw = 8 if shape not in ("C4", "C5") else 5
     cfg, H, R, k = make_walkers(shape, nw, seed=33)
     if density:
-        H, R = compress(cfg, H, R, density, 33)
+        H, R = densify(eng, oracle, cfg, shape, H, R, k, density, 33)
     seed = 515151
     limit = float(np.median([oracle.volume(H[w]) for w in range(nw)]))
     pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=CELLS | T)
@@ -131,19 +163,19 @@ def test_cells_mc_run_trajectory_bit_exact(eng, oracle, shape, T, sweeps, densit
 
 
 @pytest.mark.parametrize("shape", ["C4", "C5", "d140", "p7x"])
-def test_default_dispatch_shares_a_walk_between_kernels(eng, oracle, shape):
-    """threads_per_walker = 0 on large chain systems: the dilute walkers of the batch are walked by the warp-per-move
-    kernel, the dense ones by the cell-list kernel (two launches, each skipping the other's walkers) -- every walker is
-    walked exactly once and the result is the oracle's."""
+def test_default_dispatch_box_moves_through_cells_when_dense(eng, oracle, shape):
+    """threads_per_walker = 0 on large chain systems: in the same batch, dilute walkers test their box moves with the
+    chain-pair pass and dense ones (bounding spheres prune nothing) with a cell list of the trial configuration; the
+    result is the oracle's either way."""
     if shape == "p7x":
         SHAPES["p7x"] = (40, 7, [2, 20, 20, 10, 3, 3])   # 280 beads on the cooperative kernel: cell list per walker (mode 2)
     nw = 6
     cfg, H, R, k = make_walkers(shape, nw, seed=35)
-    dense_H, dense_R = compress(cfg, H[:3].copy(), R[:3].copy(), 0.5 if shape != "d140" else 0.4, 35)
+    dense_H, dense_R = densify(eng, oracle, cfg, shape, H[:3].copy(), R[:3].copy(), k, {"C4": 0.5, "C5": 0.3, "d140": 0.3}.get(shape, 0.45), 35)
     H[:3], R[:3] = dense_H, dense_R          # walkers 0-2 dense (rho >= 0.4), 3-5 dilute (rho = 1/15)
     N = R.shape[1]
     rho = np.array([N / oracle.volume(H[w]) for w in range(nw)])
-    assert (rho[:3] > 0.35).all() and (rho[3:] < 0.1).all()
+    assert (rho[:3] > 0.29).all() and (rho[3:] < 0.1).all()
     seed = 99
     pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=0)
     limit = 1e300
@@ -159,3 +191,30 @@ def test_default_dispatch_shares_a_walk_between_kernels(eng, oracle, shape):
     assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
     if shape == "p7x":
         del SHAPES["p7x"]
+
+
+@pytest.mark.parametrize("tpw", [0, 1, 8, 24, 28, 32, 64])
+def test_thin_cells_every_kernel_family(eng, oracle, tpw):
+    """Perpendicular widths between ~1.5 and 2.1 sigma: the float32 pre-filter switches itself off (hans_walk.cuh,
+    filter_params) and the chain-level pruning keeps everything; every kernel family must still follow the oracle."""
+    def shear(w, H):
+        d = np.zeros((3, 3))
+        d[0] = (0.9 + 0.2 * w) * H[1] + 0.4 * H[2]
+        d[2] = -0.5 * H[1]
+        return d
+    cfg, H, R, k = make_walkers("tiny", 6, seed=21, dr_max=0.5, dshear=0.3, dstretch=0.1, min_ar=0.05, min_ang=3.0)
+    H, R = compress(cfg, H, R, 0.35, 21)
+    widths = []
+    for w in range(6):
+        oracle.change_box(cfg, H[w], R[w], shear(w, H[w]))
+        Hi = np.linalg.inv(H[w])
+        widths.append(1.0 / np.sqrt((Hi ** 2).sum(axis=0)).max())
+    assert min(widths) < 2.0 and max(widths) < 3.5, widths
+    try:
+        _replay(eng, oracle, "tiny", tpw, nwalkers=6, nmoves=400, dense=0.35, squash=shear, dr_max=0.5, dshear=0.3,
+                dstretch=0.1, min_ar=0.05, min_ang=3.0)
+    except Exception as e:
+        from hans_b200 import _lib
+        if isinstance(e, _lib.HansError) and "needs" in str(e):
+            pytest.skip(str(e))
+        raise
