@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_arg
     __threadfence_system();
     __syncthreads();
     const unsigned long long want = (unsigned long long)it + 1ull;
+    __shared__ int s_expired;
+    if (threadIdx.x == 0) s_expired = 0;
+    __syncthreads();
     if ((int)threadIdx.x < world) {
         unsigned long long *f = pt.base[threadIdx.x] + (size_t)par * world + a.rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(want) : "memory");
@@ -258,11 +261,13 @@ __global__ void __launch_bounds__(512) ns_exchange_peer_kernel(const hans_ns_arg
         const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(g) : "memory");
-            // (default: wait for ever, like a collective; hans_ns_peer_timeout bounds it for tests)
-            if (spin_limit > 0 && v < want && clock64() - t0 > spin_limit) { atomicAdd(&g_diag[2], 1ull); break; }
+            // a peer that never raises its flag (a dead rank) must not hang this GPU for ever: the wait is bounded
+            // (hans_ns_peer_timeout; default 60 s), an expired wait is counted and the iteration is NOT resolved
+            if (spin_limit > 0 && v < want && clock64() - t0 > spin_limit) { atomicAdd(&g_diag[2], 1ull); s_expired = 1; break; }
         } while (v < want);
     }
     __syncthreads();
+    if (s_expired) return; // stale records: nothing is cloned, the iteration counter does not advance; the host sees diag[2]
     ns_resolve_body(a, reinterpret_cast<const double *>(pt.base[a.rank] + hdr) + (size_t)par * world * rec);
 }
 
@@ -944,7 +949,7 @@ int hans_ns_resolve(const hans_ns_args *a, void *stream)
     return HANS_OK;
 }
 
-static long long g_peer_spin_limit = 0; // SM clock cycles; 0 = no limit
+static long long g_peer_spin_limit = (long long)(60.0 * 1.9e9); // SM clock cycles (default 60 s); 0 = no limit
 int hans_ns_peer_timeout(double seconds)
 {
     g_peer_spin_limit = seconds > 0.0 ? (long long)(seconds * 1.9e9) : 0;

@@ -78,7 +78,7 @@ class NestedSampler:
 
     def __init__(self, pool: WalkerPool, nwalkers: int, walklength: int, rank: int = 0, world: int = 1,
                  group=None, seed: int = 0, start_iter: int = 0, traj_interval: int = 100, traj_slots: int = 8,
-                 log_cap: int = 8192, mc_adjust_wl: int = 10, adjust_samples: int = 128):
+                 log_cap: int = 8192, mc_adjust_wl: int = 10, adjust_samples: int = 1024):
         if pool.nwalkers % nwalkers:
             raise ValueError("pool size must be a multiple of nwalkers")
         self.pool, self.nw, self.walklength = pool, int(nwalkers), int(walklength)
@@ -87,7 +87,7 @@ class NestedSampler:
         self.nvranks = pool.nwalkers // self.nw
         self.K = pool.nwalkers * self.world  # total live walkers (mpihans.py:202)
         self.mc_adjust_wl = int(mc_adjust_wl)
-        self.adjust_samples = int(min(adjust_samples, self.nvranks))
+        self.adjust_samples = int(adjust_samples)  # virtual ranks sampled per adaptation, over ALL GPUs
         dev = pool.device
         self.rec_len = 12 + 3 * pool.N
         self.rec = torch.zeros(self.rec_len, dtype=torch.float64, device=dev)
@@ -199,6 +199,9 @@ class NestedSampler:
         if n > self.log_cap:
             raise RuntimeError("volume log ring overflowed: flush more often than log_cap iterations")
         torch.cuda.synchronize(self.pool.device)
+        if self._peer is not None and _lib.diag_counters()[2]:
+            raise _lib.HansError("peer-memory NS exchange: a wait for another rank's flag expired (dead or stalled rank); "
+                                 "the iterations since the last flush are void")
         its = np.arange(self.flushed, self.iteration, dtype=np.int64)
         log = np.zeros((n, 4))
         if n:
@@ -232,37 +235,47 @@ class NestedSampler:
                 setattr(self._scratch.cfg, k, float(steps[k]))
 
     def measure_rates(self, vol_max: Optional[float] = None) -> np.ndarray:
-        """Acceptance rate of every enabled move type from `mc_adjust_wl` single-type sweeps on
-        copies of randomly chosen local walkers under the current ceiling (MCNS.py:676-684; the
-        copies replace the backup / import_ase_to_ibox restore).  Returns [sum of rates (6),
-        number of sampled walkers] for the cross-rank average."""
-        pool, A = self.pool, self.adjust_samples
+        """Acceptance rate of every enabled move type from `mc_adjust_wl` single-type sweeps on copies of one random
+        walker of each sampled virtual rank under the current ceiling (MCNS.py:676-684; the copies replace the backup /
+        import_ase_to_ibox restore).  Returns [sum of rates (6), number of sampled virtual ranks] for the cross-rank
+        average.
+
+        Everything random here is a pure function of (seed, iteration, GLOBAL virtual rank): which virtual ranks are
+        sampled (at most `adjust_samples` of all world x nvranks), which of its walkers each one tries, and the Philox
+        stream of every trial walk (walker id 0x40000000 + 6 x global virtual rank + move type, counter positioned by
+        the iteration).  So a run resumed from a restart file, and a run laid out over another number of GPUs with
+        the same total of virtual ranks, adapt exactly like the original (the reference saves no RNG state at all)."""
+        pool, nv, nw = self.pool, self.nvranks, self.nw
+        total = nv * self.world
         if self._scratch is None:
-            self._scratch = WalkerPool(A * 6, pool.nchains, pool.nbeads, pool.move_ratio, device=pool.device,
-                                       seed=pool.seed, gid_base=0x40000000 + self.rank * A * 6,
+            self._scratch = WalkerPool(nv * 6, pool.nchains, pool.nbeads, pool.move_ratio, device=pool.device,
+                                       seed=pool.seed, gid_base=0x40000000 + self.rank * nv * 6,
                                        threads_per_walker=pool.tpw, **pool._cfg_kw)
         sc = self._scratch
         C.memmove(C.byref(sc.cfg), C.byref(pool.cfg), C.sizeof(_lib.Cfg))
-        # Everything random here is a pure function of (seed, rank, iteration): a run resumed from a restart file
-        # adapts exactly like the uninterrupted run (the reference saves no RNG state at all).  The trial walks draw
-        # from their own Philox streams (walker ids above 0x40000000), positioned by the iteration.
-        rng = np.random.default_rng([self.seed, self.rank, self.iteration, 0x5ca1ab1e])
-        sc.ctr.fill_(self.iteration << 24)
-        # one random walker of A distinct virtual ranks (MCNS.py:676)
-        vr = rng.choice(self.nvranks, size=A, replace=False)
-        picks = vr * self.nw + rng.integers(0, self.nw, size=A)
-        idx = torch.as_tensor(np.tile(picks, 6), device=pool.device)
-        sc.H.copy_(pool.H[idx])
-        sc.R.copy_(pool.R[idx])
-        limit = self.d_limit if vol_max is None else None
+        rng = np.random.default_rng([self.seed, self.iteration, 0x5ca1ab1e])
+        S = min(total, self.adjust_samples)
+        chosen = rng.choice(total, size=S, replace=False) if S < total else np.arange(total)
+        walker_of = rng.integers(0, nw, size=total)            # the walker each virtual rank would try (MCNS.py:676)
+        lo = self.rank * nv
+        mine = np.sort(chosen[(chosen >= lo) & (chosen < lo + nv)]) - lo
         sums = np.zeros(7)
+        sums[6] = len(mine)
+        if len(mine) == 0:
+            return sums
+        src = torch.as_tensor(np.repeat(mine * nw + walker_of[lo + mine], 6), device=pool.device)
+        dst = torch.as_tensor((mine[:, None] * 6 + np.arange(6)[None, :]).reshape(-1), device=pool.device)
+        sc.H[dst] = pool.H[src]
+        sc.R[dst] = pool.R[src]
+        sc.ctr.fill_(self.iteration << 24)
+        limit = self.d_limit if vol_max is None else None
         outs = []
         for i in range(6):
             if pool.move_ratio[i] == 0:
                 continue
             ratio = np.zeros(6)
             ratio[i] = 1.0  # np.eye(6)[i], MCNS.py:679-682
-            ids = torch.arange(i * A, (i + 1) * A, dtype=torch.int32, device=pool.device)
+            ids = torch.as_tensor((mine * 6 + i).astype(np.int32), device=pool.device)
             att, acc = sc.mc_run(self.mc_adjust_wl, ids=ids, d_volume_limit=limit,
                                  volume_limit=_lib.DBL_MAX if vol_max is None else float(vol_max),
                                  cfg=sc.cfg_with(ratio), count_pairs=False)
@@ -272,7 +285,6 @@ class NestedSampler:
         for i, att, acc in outs:
             a = att[:, i].double().clamp(min=1.0)  # MCNS.py:384
             sums[i] = float((acc[:, i].double() / a).sum().item())
-        sums[6] = A
         return sums
 
     def adjust_mc_steps(self, vol_max: Optional[float] = None, lower_bound=0.2, upper_bound=0.5):

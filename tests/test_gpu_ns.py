@@ -266,3 +266,45 @@ def test_order_parameters_from_trajectory_file(eng, tmp_path):
     assert np.allclose(nematic.trans_order_param(frames, 6, 16), op.trans_order_param(cells, pos, 6, 16), atol=1e-10)
     # wrapping atoms does not change the nematic order (minimum-image end-to-end vectors)
     assert np.allclose(nematic.nematic_order_param(frames, 6, 16), pool.order_parameters()[0].cpu().numpy(), atol=1e-9)
+
+
+# ---- a20: the step adaptation's acceptance rates against the oracle on the same walkers -------------------------------
+@pytest.mark.parametrize("nchains,nbeads,mr,nw_per,nv", [(8, 4, [3, 24, 16, 8, 3, 3], 3, 6), (20, 1, [1, 60, 0, 0, 3, 3], 1, 12)])
+def test_measure_rates_equals_oracle_single_type_walks(eng, oracle, nchains, nbeads, mr, nw_per, nv):
+    """adjust_mc_steps (MCNS.py:657-717): for every enabled move type, `mc_adjust_wl` single-type sweeps on a copy of one
+    walker of every (sampled) virtual rank under the current ceiling; the summed acceptance rates must be exactly what the
+    oracle gets for the same walkers, streams (walker id 0x40000000 + 6 v + type, counter = iteration << 24) and step
+    sizes -- and the walkers themselves must be left untouched (MCNS.py:683 restores the backup)."""
+    from hans_b200.ns import NestedSampler, update_steps
+    seed = 77
+    pool = _pool(eng, nw_per * nv, nchains, nbeads, mr, seed=seed)
+    pool.mc_run(4, counters=False)
+    ns = NestedSampler(pool, nwalkers=nw_per, walklength=2, seed=seed, traj_interval=0, mc_adjust_wl=3)
+    ns.run(5)
+    torch.cuda.synchronize()
+    H0, R0 = pool.get_state()
+    limit = ns.volume_limit()
+    steps0 = ns.steps()
+    sums = ns.measure_rates()
+    H1, R1 = pool.get_state()
+    assert np.array_equal(H0, H1) and np.array_equal(R0, R1)
+    # the same thing with the oracle
+    rng = np.random.default_rng([seed, ns.iteration, 0x5ca1ab1e])
+    walker_of = rng.integers(0, nw_per, size=nv)          # (all nv virtual ranks are sampled: nv <= adjust_samples)
+    want = np.zeros(7)
+    want[6] = nv
+    for i in range(6):
+        if mr[i] == 0:
+            continue
+        ratio = np.zeros(6); ratio[i] = 1.0
+        cfg = oracle.make_cfg(nchains, nbeads, ratio, **steps0)
+        for v in range(nv):
+            w = v * nw_per + int(walker_of[v])
+            Hc, Rc = H0[w].copy(), R0[w].copy()
+            _, att, acc, _ = oracle.mc_run(cfg, Hc, Rc, 3, limit, seed, 0x40000000 + 6 * v + i, ns.iteration << 24)
+            want[i] += acc[i] / max(att[i], 1)
+    assert np.allclose(sums, want, rtol=0, atol=1e-12), (sums, want)
+    # and the rule applied to them (MCNS.py:687-716)
+    avg = ns.adjust_mc_steps()
+    assert np.allclose(avg, want[:6] / nv, atol=1e-12)
+    assert ns.steps() == update_steps(steps0, avg, np.asarray(mr, dtype=float))
