@@ -411,12 +411,31 @@ static int sm_count()
     return n;
 }
 
+constexpr size_t SMEM_MAX = 227 * 1024;
+
 template <typename K> static int prep_kernel(K kernel, size_t smem)
 {
-    if (smem > 227 * 1024) return fail(HANS_ELIMIT, "walker does not fit in shared memory (cell-list path not built yet)");
+    if (smem > SMEM_MAX) return fail(HANS_ELIMIT, "walker does not fit in shared memory for this kernel family");
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return HANS_OK;
 }
+
+// Walkers beyond 227 KB: the same kernels with the walker state in a per-CTA region of GLOBAL memory (namespace hbg,
+// hans_walk_body.inc).  The regions are a stream-ordered allocation that lives for the launch.
+struct BigState {
+    double *base = nullptr;
+    unsigned long long stride = 0; // doubles per CTA
+    int grid = 0;
+};
+static int big_alloc(BigState &b, size_t bytes_per_cta, int ctas_wanted, cudaStream_t st)
+{
+    const int cap = sm_count() * 4;
+    b.grid = ctas_wanted < cap ? (ctas_wanted > 0 ? ctas_wanted : 1) : cap;
+    b.stride = (bytes_per_cta + 255) / 256 * 32; // doubles, 256-byte aligned regions
+    CK(cudaMallocAsync((void **)&b.base, (size_t)b.grid * b.stride * sizeof(double), st));
+    return HANS_OK;
+}
+static void big_free(BigState &b, cudaStream_t st) { if (b.base) cudaFreeAsync(b.base, st); b.base = nullptr; }
 
 static int grid_for(int n, int T)
 {
@@ -622,6 +641,21 @@ static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory,
 {
     int rc = HANS_OK;
     const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode);
+    if (smem > SMEM_MAX) { // state in global memory
+        BigState b;
+        rc = big_alloc(b, smem, (a.n_active + (T == 32 ? 3 : 0)) / (T == 32 ? 4 : 1), st);
+        if (rc) return rc;
+        hbg::WalkArgs g;
+        static_assert(sizeof(hbg::WalkArgs) == sizeof(WalkArgs), "the two state spaces share the argument layout");
+        memcpy(&g, &a, sizeof g);
+        g.state_base = b.base; g.state_stride = b.stride;
+        if (from_memory) { DISPATCH_T(T, { hbg::walk_kernel<TT, true><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
+        else { DISPATCH_T(T, { hbg::walk_kernel<TT, false><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
+        const cudaError_t e = cudaGetLastError();
+        big_free(b, st);
+        if (e != cudaSuccess) return cuda_fail(e, "walk_kernel (state in global memory)");
+        return HANS_OK;
+    }
     if (from_memory) {
         DISPATCH_T(T, {
             rc = prep_kernel(walk_kernel<TT, true>, smem);
@@ -676,6 +710,12 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
     }
     const int T = pick_T(cfg, threads_per_walker);
     if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 1, 8, 24, 28, 32, 64, 128 or 256 (optionally | HANS_TPW_CELLS)");
+    if (dflt && cta_smem_bytes(cfg, T) > SMEM_MAX) {
+        // a walker that does not fit shared memory: state in global memory, and the per-walker cell list for every overlap
+        // test (all pairs of thousands of beads is what the list is for)
+        a.cells_mode = 1;
+        return launch_coop(cfg, a, from_memory, 256, st);
+    }
     if (dflt && cfg->nchains * cfg->nbeads >= 192 && cells_fit(cfg, T, 2) && rho_split() > 0.0) {
         a.cells_mode = 2; // box moves of dense trial configurations through the cell list
         a.rho_split = rho_split();
@@ -805,10 +845,19 @@ int hans_check_overlap(const hans_cfg *cfg, const double *d_H, const double *d_R
     if (T < 0) return fail(HANS_EINVAL, "threads_per_walker must be 0, 32, 64, 128 or 256");
     const size_t smem = cta_smem_bytes(cfg, T);
     cudaStream_t st = (cudaStream_t)stream;
+    if (smem > SMEM_MAX) {
+        BigState b;
+        rc = big_alloc(b, smem, (n + (T == 32 ? 3 : 0)) / (T == 32 ? 4 : 1), st);
+        if (rc) return rc;
+        DISPATCH_T(T, { hbg::overlap_kernel<TT><<<b.grid, cta_threads<TT>(), 16, st>>>(*cfg, d_H, d_R, d_ids, n, inter_only, d_out, b.base, b.stride); });
+        big_free(b, st);
+        CK(cudaGetLastError());
+        return HANS_OK;
+    }
     DISPATCH_T(T, {
         rc = prep_kernel(overlap_kernel<TT>, smem);
         if (rc) return rc;
-        overlap_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, inter_only, d_out);
+        overlap_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, inter_only, d_out, nullptr, 0);
     });
     CK(cudaGetLastError());
     return HANS_OK;
@@ -835,10 +884,19 @@ int hans_change_box(const hans_cfg *cfg, double *d_H, double *d_R, const int32_t
     const int T = pick_T(cfg, 0);
     const size_t smem = cta_smem_bytes(cfg, T);
     cudaStream_t st = (cudaStream_t)stream;
+    if (smem > SMEM_MAX) {
+        BigState b;
+        rc = big_alloc(b, smem, (n + (T == 32 ? 3 : 0)) / (T == 32 ? 4 : 1), st);
+        if (rc) return rc;
+        DISPATCH_T(T, { hbg::change_box_kernel<TT><<<b.grid, cta_threads<TT>(), 16, st>>>(*cfg, d_H, d_R, d_ids, n, d_dH, b.base, b.stride); });
+        big_free(b, st);
+        CK(cudaGetLastError());
+        return HANS_OK;
+    }
     DISPATCH_T(T, {
         rc = prep_kernel(change_box_kernel<TT>, smem);
         if (rc) return rc;
-        change_box_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, d_dH);
+        change_box_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, d_dH, nullptr, 0);
     });
     CK(cudaGetLastError());
     return HANS_OK;
@@ -862,11 +920,21 @@ static int launch_grow(const hans_cfg *cfg, const double *d_H, double *d_R, cons
     const size_t smem = cta_smem_bytes(cfg, T);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = HANS_OK;
+    if (smem > SMEM_MAX) {
+        BigState b;
+        rc = big_alloc(b, smem, (n + (T == 32 ? 3 : 0)) / (T == 32 ? 4 : 1), st);
+        if (rc) return rc;
+        DISPATCH_T(T, { hbg::grow_kernel<TT><<<b.grid, cta_threads<TT>(), 16, st>>>(*cfg, d_H, d_R, d_ids, n, seed, gid_base, cb, ce, attempt0,
+                                                                               max_attempts, d_status, b.base, b.stride); });
+        big_free(b, st);
+        CK(cudaGetLastError());
+        return HANS_OK;
+    }
     DISPATCH_T(T, {
         rc = prep_kernel(grow_kernel<TT>, smem);
         if (rc) return rc;
         grow_kernel<TT><<<grid_for(n, TT), cta_threads<TT>(), smem, st>>>(*cfg, d_H, d_R, d_ids, n, seed, gid_base, cb, ce,
-                                                                          attempt0, max_attempts, d_status);
+                                                                          attempt0, max_attempts, d_status, nullptr, 0);
     });
     CK(cudaGetLastError());
     return HANS_OK;

@@ -36,7 +36,7 @@ def assert_state_equal(pool, H, R):
     assert bad.size == 0, f"bead coordinates differ from oracle for walkers {bad[:8]}"
 
 
-def densify(eng, oracle, cfg, shape, H, R, k, density, seed, max_rounds=900, shrink=0.985):
+def densify(eng, oracle, cfg, shape, H, R, k, density, seed, max_rounds=900, shrink=0.985, prep_tpw=128):
     """Walkers at a bead number density.  Small walkers: the oracle's own shrink / relax loop (tests/common.py).  Large
     ones (hundreds of beads: minutes on the CPU): the same procedure on the device with the plain cooperative kernel
     (threads_per_walker = 128, no cell list) -- only a way to MAKE dense start states; the comparison that follows is
@@ -45,7 +45,7 @@ def densify(eng, oracle, cfg, shape, H, R, k, density, seed, max_rounds=900, shr
     if N < 200:
         return compress(cfg, H, R, density, seed)
     nchains, nbeads, mr = SHAPES[shape]
-    pool = make_pool(eng, shape, H, R, k, seed=seed + 1000, tpw=128)
+    pool = make_pool(eng, shape, H, R, k, seed=seed + 1000, tpw=prep_tpw)
     relax = pool.cfg_with([0.0] + [float(x) for x in mr[1:4]] + [0.0, 0.0])
     relax.dr_max, relax.dt_max, relax.dh_max = 0.3, 0.3, 0.3
     nw = H.shape[0]
@@ -68,10 +68,11 @@ def densify(eng, oracle, cfg, shape, H, R, k, density, seed, max_rounds=900, shr
     return H2, R2
 
 
-def _replay(eng, oracle, shape, tpw, nwalkers=8, nmoves=400, seed=21, dense=None, mode=0, squash=None, **kw):
-    cfg, H, R, k = make_walkers(shape, nwalkers, seed=seed, **kw)
+def _replay(eng, oracle, shape, tpw, nwalkers=8, nmoves=400, seed=21, dense=None, mode=0, squash=None, presweeps=2, prep_tpw=128,
+            **kw):
+    cfg, H, R, k = make_walkers(shape, nwalkers, seed=seed, presweeps=presweeps, **kw)
     if dense:
-        H, R = densify(eng, oracle, cfg, shape, H, R, k, dense, seed)
+        H, R = densify(eng, oracle, cfg, shape, H, R, k, dense, seed, prep_tpw=prep_tpw)
     if squash is not None:   # affine squash of cell and beads along one axis would overlap; shear instead (volume kept)
         for w in range(nwalkers):
             oracle.change_box(cfg, H[w], R[w], squash(w, H[w]))
@@ -218,3 +219,59 @@ def test_thin_cells_every_kernel_family(eng, oracle, tpw):
         if isinstance(e, _lib.HansError) and "needs" in str(e):
             pytest.skip(str(e))
         raise
+
+
+# ---- walkers that do not fit the 227 KB of shared memory: state in global memory + cell list -------------------------
+BIG = (512, 6, [2, 6, 6, 3, 2, 2])   # 3 072 beads: ~260 KB of walker state
+
+
+@pytest.mark.parametrize("tpw,density", [(0, None), (0, 0.11), (CELLS | 256, 0.11), (128, None), (CELLS | 32, None)])
+def test_walker_beyond_shared_memory_replay(eng, oracle, tpw, density):
+    """3 072 beads per walker: the kernels run with the walker state in a per-CTA region of global memory (namespace hbg)
+    and, by default, the per-walker cell list for every overlap test.  Explicit proposals of every move type, at the
+    initial density and compressed (1.6 x the bead density; further compression of 3 072 beads takes minutes): decisions, reasons, weights and the post-move state equal the all-pairs oracle's, bit for bit."""
+    import ctypes as C
+    from hans_b200 import _lib
+    SHAPES["big"] = BIG
+    try:
+        assert _lib.lib.hans_walker_smem_bytes(C.byref(_lib.make_cfg(BIG[0], BIG[1], BIG[2]))) > 227 * 1024
+        # (no oracle pre-walk: two sweeps of 5 127 all-pairs moves take minutes on the CPU; dense states are prepared on
+        # the device with the cell-list kernel and then checked free of overlaps by the oracle)
+        props, dec = _replay(eng, oracle, "big", tpw, nwalkers=2, nmoves=160, seed=41, dense=density, presweeps=0,
+                             prep_tpw=CELLS | 256, dr_max=0.6 if density else 2.0, dv_max=60.0, dshear=0.2, dstretch=0.05)
+        assert set(np.unique(props["type"])) >= {0, 1, 2, 3, 4, 5} and 0 < dec["accepted"].mean() < 1
+    finally:
+        del SHAPES["big"]
+
+
+def test_walker_beyond_shared_memory_walk(eng, oracle):
+    """Growth, overlap predicate, change_box and a self-driving walk for the same walker size (all through the
+    global-memory state path), against the oracle."""
+    SHAPES["big"] = BIG
+    try:
+        nchains, nbeads, mr = BIG
+        nw, seed = 2, 4242
+        pool = eng.WalkerPool(nw, nchains, nbeads, mr, seed=seed)
+        pool.set_initial_cells()
+        pool.grow()
+        cfg = oracle.make_cfg(nchains, nbeads, mr)
+        H, R = oracle.grow_walkers(cfg, nw, seed)
+        assert_state_equal(pool, H, R)
+        assert not pool.check_overlap().cpu().numpy().any()
+        dH = np.array([[[0.3, 0.1, 0.0], [0.0, -0.2, 0.4], [0.2, 0.0, 0.1]]] * nw)
+        pool.change_box([0, 1], dH)
+        for w in range(nw):
+            oracle.change_box(cfg, H[w], R[w], dH[w])
+        assert_state_equal(pool, H, R)
+        got = pool.check_overlap().cpu().numpy()
+        assert np.array_equal(got, [oracle.check_overlap(cfg, H[w], R[w]) for w in range(nw)])
+        # a self-driving walk of 300 moves (hans_mc_run_batch walks whole sweeps of 5 127 moves: replay its proposals)
+        nm = 300
+        props = np.stack([oracle.gen_proposals(cfg, seed, w, 0, nm) for w in range(nw)])
+        limit = float(max(oracle.volume(H[w]) for w in range(nw)))
+        got = pool.replay(None, props, volume_limit=limit)
+        want = np.stack([oracle.replay(cfg, H[w], R[w], props[w], limit) for w in range(nw)])
+        assert np.array_equal(got["accepted"], want["accepted"]) and np.array_equal(got["reason"], want["reason"])
+        assert_state_equal(pool, H, R)
+    finally:
+        del SHAPES["big"]
