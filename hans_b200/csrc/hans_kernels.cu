@@ -529,11 +529,17 @@ template <bool REPLAY> static int launch_team(WalkArgs a, int nwarp, cudaStream_
     const size_t smem = team_smem_bytes(c, nwarp, a.cells_mode == 2);
     const int cap = sm_count() * 8, grid = a.n_active < cap ? a.n_active : cap;
     int rc = HANS_OK;
-#define TEAM_LAUNCH(NN, WW)                                                        \
-    {                                                                              \
-        rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY>, smem);                  \
-        if (rc) return rc;                                                         \
-        walk_team_kernel<NN, WW, REPLAY><<<grid, 32 * WW, smem, st>>>(a);          \
+#define TEAM_LAUNCH(NN, WW)                                                                 \
+    {                                                                                       \
+        if (a.cells_mode == 2) {                                                            \
+            rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY, true>, smem);                 \
+            if (rc) return rc;                                                              \
+            walk_team_kernel<NN, WW, REPLAY, true><<<grid, 32 * WW, smem, st>>>(a);         \
+        } else {                                                                            \
+            rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY, false>, smem);                \
+            if (rc) return rc;                                                              \
+            walk_team_kernel<NN, WW, REPLAY, false><<<grid, 32 * WW, smem, st>>>(a);        \
+        }                                                                                   \
     }
 #define TEAM_NB(WW)                                                                \
     switch (c->nbeads) {                                                           \
@@ -649,28 +655,37 @@ static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory,
         static_assert(sizeof(hbg::WalkArgs) == sizeof(WalkArgs), "the two state spaces share the argument layout");
         memcpy(&g, &a, sizeof g);
         g.state_base = b.base; g.state_stride = b.stride;
-        if (from_memory) { DISPATCH_T(T, { hbg::walk_kernel<TT, true><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
-        else { DISPATCH_T(T, { hbg::walk_kernel<TT, false><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
+        if (from_memory) { DISPATCH_T(T, { hbg::walk_kernel<TT, true, true><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
+        else { DISPATCH_T(T, { hbg::walk_kernel<TT, false, true><<<b.grid, cta_threads<TT>(), 16, st>>>(g); }); }
         const cudaError_t e = cudaGetLastError();
         big_free(b, st);
         if (e != cudaSuccess) return cuda_fail(e, "walk_kernel (state in global memory)");
         return HANS_OK;
     }
-    if (from_memory) {
-        DISPATCH_T(T, {
-            rc = prep_kernel(walk_kernel<TT, true>, smem);
-            if (rc) return rc;
-            walk_kernel<TT, true><<<grid_for(a.n_active, TT), cta_threads<TT>(), smem, st>>>(a);
-        });
-    } else {
-        DISPATCH_T(T, {
-            rc = prep_kernel(walk_kernel<TT, false>, smem);
-            if (rc) return rc;
-            walk_kernel<TT, false><<<grid_for(a.n_active, TT), cta_threads<TT>(), smem, st>>>(a);
-        });
-    }
+#define COOP_LAUNCH(RP, CLV)                                                                                  \
+    DISPATCH_T(T, {                                                                                           \
+        rc = prep_kernel(walk_kernel<TT, RP, CLV>, smem);                                                     \
+        if (rc) return rc;                                                                                    \
+        walk_kernel<TT, RP, CLV><<<grid_for(a.n_active, TT), cta_threads<TT>(), smem, st>>>(a);               \
+    })
+    if (a.cells_mode) { if (from_memory) { COOP_LAUNCH(true, true); } else { COOP_LAUNCH(false, true); } }
+    else { if (from_memory) { COOP_LAUNCH(true, false); } else { COOP_LAUNCH(false, false); } }
+#undef COOP_LAUNCH
     CK(cudaGetLastError());
     return HANS_OK;
+}
+
+// Can a box move of this shape ever take the cell-list branch of move_box?  It needs the reach of a pair of chains
+// (two bounding radii of a zig-zag chain + sigma) to exceed half the cell width at a bead density a hard-sphere chain
+// fluid can reach; shapes that cannot (short chains: C5's hexamers would need rho = 3.7) keep the kernels without the
+// list code (instruction-cache footprint).
+static bool box_cells_can_pay(const hans_cfg *c)
+{
+    const int N = c->nchains * c->nbeads;
+    if (N < 192 || c->nbeads < 2) return false;
+    const double reach = 2.0 * 0.82 * c->bondlength * (double)(c->nbeads >> 1) + 1.0;
+    const double rho_crit = (double)N / ((2.0 * reach) * (2.0 * reach) * (2.0 * reach));
+    return rho_crit < 1.0;
 }
 
 // does the cell-list kernel fit shared memory for this shape (with T threads per walker)?
@@ -694,11 +709,18 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         const int nwarp = threads_per_walker - 20;
         if (!team_applies(cfg, nwarp))
             return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
-        if (dflt && rho_split() > 0.0 && cfg->nchains * cfg->nbeads >= 192) {
-            // default for large chain systems: box moves of DENSE trial configurations (where bounding spheres prune nothing
-            // and the chain-pair pass degenerates to all pairs) go through a cell list of the trial configuration
-            a.cells_mode = 2;
-            a.rho_split = rho_split();
+        if (dflt && rho_split() > 0.0 && box_cells_can_pay(cfg)) {
+            // default for large chain systems with long chains: box moves of DENSE trial configurations (where bounding
+            // spheres prune nothing and the chain-pair pass degenerates to all pairs) go through a cell list of the trial
+            // configuration.  The kernel that carries that code is 10 % slower on dilute walkers (code size), so the walk
+            // is launched as both kernels and the ceiling decides which one runs (WalkArgs::launch_side).
+            WalkArgs lo = a, hi = a;
+            lo.launch_side = 1; hi.launch_side = 2;
+            lo.rho_split = hi.rho_split = rho_split();
+            hi.cells_mode = 2;
+            int rc = from_memory ? launch_team<true>(lo, nwarp, st) : launch_team<false>(lo, nwarp, st);
+            if (rc) return rc;
+            return from_memory ? launch_team<true>(hi, nwarp, st) : launch_team<false>(hi, nwarp, st);
         }
         return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
     }
@@ -716,9 +738,14 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         a.cells_mode = 1;
         return launch_coop(cfg, a, from_memory, 256, st);
     }
-    if (dflt && cfg->nchains * cfg->nbeads >= 192 && cells_fit(cfg, T, 2) && rho_split() > 0.0) {
-        a.cells_mode = 2; // box moves of dense trial configurations through the cell list
-        a.rho_split = rho_split();
+    if (dflt && box_cells_can_pay(cfg) && cells_fit(cfg, T, 2) && rho_split() > 0.0) {
+        WalkArgs lo = a, hi = a; // (as for the warp-per-move kernel above)
+        lo.launch_side = 1; hi.launch_side = 2;
+        lo.rho_split = hi.rho_split = rho_split();
+        hi.cells_mode = 2;
+        const int rc = launch_coop(cfg, lo, from_memory, T, st);
+        if (rc) return rc;
+        return launch_coop(cfg, hi, from_memory, T, st);
     }
     return launch_coop(cfg, a, from_memory, T, st);
 }

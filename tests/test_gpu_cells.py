@@ -163,35 +163,34 @@ def test_cells_mc_run_trajectory_bit_exact(eng, oracle, shape, T, sweeps, densit
     assert not pool.check_overlap().cpu().numpy().any()
 
 
-@pytest.mark.parametrize("shape", ["C4", "C5", "d140", "p7x"])
-def test_default_dispatch_box_moves_through_cells_when_dense(eng, oracle, shape):
-    """threads_per_walker = 0 on large chain systems: in the same batch, dilute walkers test their box moves with the
-    chain-pair pass and dense ones (bounding spheres prune nothing) with a cell list of the trial configuration; the
-    result is the oracle's either way."""
-    if shape == "p7x":
-        SHAPES["p7x"] = (40, 7, [2, 20, 20, 10, 3, 3])   # 280 beads on the cooperative kernel: cell list per walker (mode 2)
-    nw = 6
-    cfg, H, R, k = make_walkers(shape, nw, seed=35)
-    dense_H, dense_R = densify(eng, oracle, cfg, shape, H[:3].copy(), R[:3].copy(), k, {"C4": 0.5, "C5": 0.3, "d140": 0.3}.get(shape, 0.45), 35)
-    H[:3], R[:3] = dense_H, dense_R          # walkers 0-2 dense (rho >= 0.4), 3-5 dilute (rho = 1/15)
-    N = R.shape[1]
-    rho = np.array([N / oracle.volume(H[w]) for w in range(nw)])
-    assert (rho[:3] > 0.29).all() and (rho[3:] < 0.1).all()
-    seed = 99
-    pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=0)
-    limit = 1e300
-    for sweeps in (1, 1):
-        att, acc = pool.mc_run(sweeps, volume_limit=limit)
-        ctrs_before = pool.ctr.cpu().numpy().copy()
-    ctrs = np.zeros(nw, dtype=np.uint64)
-    for sweeps in (1, 1):
-        o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, np.arange(nw), sweeps, limit, seed, np.arange(nw), ctrs)
-    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
-    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
-    assert_state_equal(pool, H, R)
-    assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
-    if shape == "p7x":
-        del SHAPES["p7x"]
+@pytest.mark.parametrize("shape,density,ceiling", [("C4", 0.5, True), ("C4", 0.5, False), ("L16", 0.45, True), ("p16", 0.45, True),
+                                                   ("C5", 0.3, True), ("d140", 0.3, True)])
+def test_default_dispatch_dense_walkers(eng, oracle, shape, density, ceiling):
+    """threads_per_walker = 0 on large chain systems.  Long chains (C4's 12-mers, 16-mers) under a ceiling that makes every
+    walker dense: the walk is launched as two kernels and the one whose box moves go through a cell list of the trial
+    configuration runs (WalkArgs::launch_side); without a ceiling, or for short chains (C5, dimers: bounding spheres keep
+    pruning), the plain kernel runs.  Either way the result is the oracle's, and every walker is walked exactly once."""
+    SHAPES["L16"] = (24, 16, [3, 24, 24, 12, 3, 3])    # warp-per-move kernel (>= 24 chains)
+    SHAPES["p16"] = (14, 16, [3, 14, 14, 8, 3, 3])     # 224 beads, 14 chains: cooperative kernel
+    try:
+        nw = 5
+        cfg, H, R, k = make_walkers(shape, nw, seed=35)
+        H, R = densify(eng, oracle, cfg, shape, H, R, k, density, 35)
+        seed = 99
+        pool = make_pool(eng, shape, H, R, k, seed=seed, tpw=0)
+        limit = float(max(oracle.volume(H[w]) for w in range(nw))) * 1.0001 if ceiling else 1e300
+        ctrs = np.zeros(nw, dtype=np.uint64)
+        for sweeps in (1, 1):
+            att, acc = pool.mc_run(sweeps, volume_limit=limit)
+            o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, np.arange(nw), sweeps, limit, seed, np.arange(nw), ctrs)
+            assert np.array_equal(att.cpu().numpy().astype(np.uint64), o_att)
+            assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+        assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+        assert_state_equal(pool, H, R)
+        assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
+        assert o_att[:, [0, 4, 5]].sum() > 0        # box moves were part of the walk
+    finally:
+        del SHAPES["L16"], SHAPES["p16"]
 
 
 @pytest.mark.parametrize("tpw", [0, 1, 8, 24, 28, 32, 64])

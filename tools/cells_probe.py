@@ -32,7 +32,8 @@ def main():
         mps = pool.moves_per_sweep
         tvars = variants or ([24, 28, 128] if N < 700 else [28, 128]) + [CELLS | 64, CELLS | 128, CELLS | 256]
         all_ids = torch.arange(nw, dtype=torch.int32, device=dev)
-        for rho_target in [0.0, 0.12, 0.2, 0.3, 0.4, 0.55, 0.7]:
+        rungs = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0.0, 0.12, 0.2, 0.3, 0.4, 0.55, 0.7]
+        for rho_target in rungs:
             it = 0
             relax = pool.cfg_with([0.0] + [float(x) for x in mr[1:]])
             while float((N / pool.vol).median().item()) < rho_target and it < 500:
