@@ -1,6 +1,7 @@
 /*
  * hans_oracle.c -- CPU oracle (float64, scalar) for the hans nested-sampling MC walker path.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED against the real hs_alkane -- see hans_oracle.h.
+ * TEST INFRASTRUCTURE ONLY.  Parity: pinned to the reference's own Python executed live (tests/test_reference_live_cpu.py),
+ * unpinned for hs_alkane's Fortran internals [A1..A10] -- see hans_oracle.h.
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off; fused operations are explicit hd_fma()).
  */

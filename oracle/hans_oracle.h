@@ -4,19 +4,25 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under hans_b200/ may include, link, import or execute this;
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED.  The arithmetic of the reference hot path lives in the third-party Fortran
- * package hs_alkane (imported at /root/reference/NesSa/MCNS.py:2, no version pinned, source not
- * under /root/reference, gfortran/swig absent in this image), so this file restates
- *   (1) verbatim, the parts the reference spells out in Python: the MC_run control flow
- *       (NesSa/MCNS.py:276-392), shear and stretch moves (MCNS.py:135-252), the cell-shape
- *       predicates (MCNS.py:97-133), moves_per_sweep (MCNS.py:296-301);
- *   (2) from hs_alkane's published algorithm (hard spheres of diameter 1, triclinic minimum
- *       image through the reciprocal cell, rigid-chain translate / quaternion rotate / dihedral
- *       bond rotation, isotropic volume move with chains following by their first bead), the
- *       entry points MC_run calls; every place where the real Fortran might differ is listed
- *       as assumption A1..A10 in DESIGN.md and flagged "[A#]" below.
- * There are no golden vectors for this path in the reference (it has no tests); the oracle is
- * pinned instead by the physical known-answer tests in tests/ (see DESIGN.md section "Oracle").
+ * PARITY: PINNED to everything the reference itself computes, UNPINNED for hs_alkane's internals.
+ *   (1) The parts the reference spells out in Python -- the MC_run control flow (NesSa/MCNS.py:276-392: move and chain
+ *       selection, draw order and count, accept / revert / ceiling logic, rate bookkeeping), the shear and stretch moves
+ *       (MCNS.py:135-252: delta_H, rejection order), the cell-shape predicates (MCNS.py:97-133), moves_per_sweep
+ *       (MCNS.py:296-301), the step-size rule (MCNS.py:687-716), default_move_ratio (MCNS.py:610-626) -- are pinned by
+ *       EXECUTING the unmodified /root/reference/NesSa/MCNS.py in the build container on scripted random draws and
+ *       comparing with this file (tests/test_reference_live_cpu.py, tests/ref_live.py); the vectors travel as
+ *       tests/golden/ref_live_replay.npz / ref_live_trace.json (tests/golden/make_ref_live_golden.py) and are checked on
+ *       the CPU (tests/test_oracle_cpu.py) and on the B200 (tests/test_gpu_reference_golden.py).  Bit-exact, with one
+ *       stated exception: the stretch move's np.exp is libm's, this file (like the device) uses the deterministic hd_exp
+ *       (<= 2 ulp apart); with that single substitution whole runs are bit-identical, without it decisions are identical
+ *       and states agree to 1e-13.  The shear path evaluates np.dot the way numpy does in this image (FMA chain).
+ *   (2) The entry points MC_run calls INTO hs_alkane (third-party Fortran, imported at MCNS.py:2, no version pinned,
+ *       source not under /root/reference, gfortran / swig absent in this image) are restated from its published
+ *       algorithm: hard spheres of diameter 1, triclinic minimum image through the reciprocal cell, rigid-chain
+ *       translate / quaternion rotate / dihedral bond rotation, isotropic volume move with chains following by their
+ *       first bead.  Every place where the real Fortran might differ is listed as assumption A1..A10 in DESIGN.md and
+ *       flagged "[A#]" below; these remain unpinned until a box with hs_alkane exists.  They are constrained by the
+ *       physical known-answer tests in tests/ (Carnahan-Starling equation of state, rigid bonds, volume preservation).
  *
  * Conventions: float64 throughout; H is a 3x3 cell, ROWS are the cell vectors
  * (MCNS.py:112-113, :50); positions are Cartesian row vectors, r = s.H; R is

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs; never by anything under hans_b200/.
-PARITY UNPINNED against the real hs_alkane (see oracle/hans_oracle.h).
+Parity: pinned to the reference's own Python executed live (tests/test_reference_live_cpu.py); unpinned for
+hs_alkane's Fortran internals (see oracle/hans_oracle.h).
 """
 from __future__ import annotations
 
