@@ -541,7 +541,7 @@ def run_b200(args):
                                          "instruction-fetch bound, not HBM bound (DESIGN.md section 3)"},
                          "kernel": walk_kernel_name, "kernel_ms_per_launch": kernel_ms,
                          "kernel_share_of_step": kernel_ms / (ms / args.steps),
-                         "peak_source": "FFMA issue-rate probe (hans_ffma_peak, 64 FFMAs per loop trip, best of 3) run in this "
+                         "peak_source": "FFMA issue-rate probe (hans_ffma_peak, 256 FFMAs per loop trip, best of 3) run in this "
                                         "process; MEASURED_PEAKS.json holds no FP32 figure; nominal 148 SMs x 128 lanes x 2 x "
                                         "1.965 GHz = 74.4 TFLOP/s"},
             "cpu_baseline": cpu,

@@ -345,9 +345,9 @@ __global__ void order_kernel(const hans_cfg cfg, const double *gH, const double 
     }
 }
 
-// FP32 FFMA issue-rate probe (roofline denominator): 16 independent accumulators, 64 FFMAs per loop trip, so the
-// loop overhead (compare + branch + counter) is < 5 % of the issue slots
-#define HANS_FFMA_PER_TRIP 64
+// FP32 FFMA issue-rate probe (roofline denominator): 16 independent accumulators, 256 FFMAs per loop trip, so the
+// loop overhead (compare + branch + counter) is ~1 % of the issue slots
+#define HANS_FFMA_PER_TRIP 256
 __global__ void __launch_bounds__(256) ffma_kernel(int iters, float *sink)
 {
     float a[16];
@@ -487,14 +487,17 @@ template <bool REPLAY> static int launch_lean(const WalkArgs &a, int W, cudaStre
     const size_t smem = walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32) + window_smem_bytes(c->nbeads, W > 1 ? W : 0) +
                         cta_extra_bytes(c->nbeads, c->nexclude);
     int rc = HANS_OK;
-#define LEAN_LAUNCH(WW)                                                                   \
-    DISPATCH_NB(c->nbeads, {                                                              \
-        rc = prep_kernel(walk_lean_kernel<NN, WW, REPLAY>, smem);                         \
-        if (rc) return rc;                                                                \
-        walk_lean_kernel<NN, WW, REPLAY><<<spec_grid(a.n_active), 32, smem, st>>>(a);     \
+#define LEAN_LAUNCH(WW, MB)                                                                   \
+    DISPATCH_NB(c->nbeads, {                                                                  \
+        rc = prep_kernel(walk_lean_kernel<NN, WW, REPLAY, MB>, smem);                         \
+        if (rc) return rc;                                                                    \
+        walk_lean_kernel<NN, WW, REPLAY, MB><<<spec_grid(a.n_active), 32, smem, st>>>(a);     \
     })
-    if (W == 1) { LEAN_LAUNCH(1); }
-    else { LEAN_LAUNCH(8); }
+    // more walkers than fit the chip at once with the uncapped register allocation (8 one-warp CTAs per SM): the
+    // 128-register build keeps twice as many in flight
+    const bool many = a.n_active > sm_count() * 10;
+    if (W == 1) { if (many) { LEAN_LAUNCH(1, 16); } else { LEAN_LAUNCH(1, 1); } }
+    else { LEAN_LAUNCH(8, 1); }
 #undef LEAN_LAUNCH
     CK(cudaGetLastError());
     return HANS_OK;

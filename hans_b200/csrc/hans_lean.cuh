@@ -309,12 +309,13 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
     return nw;
 }
 
-// W = 1: strictly one move at a time; W = 4 / 8: speculative windows of up to W moves
-#ifndef HANS_LEAN_MIN_CTAS
-#define HANS_LEAN_MIN_CTAS 1
-#endif
-template <int NB, int W, bool REPLAY>
-__global__ void __launch_bounds__(32, HANS_LEAN_MIN_CTAS) walk_lean_kernel(const WalkArgs a)
+// W = 1: strictly one move at a time; W = 8: speculative windows of up to W moves.
+// MINB = resident one-warp CTAs per SM the register allocation must allow.  1: no cap (198 registers for hexamers: 8
+// walkers per SM) -- fastest while the batch fits the chip at once (1 024 walkers per GPU: 6.9 per SM); 16: 128 registers,
+// slower per walker (C3 -13 %, C2 -20 % at 1 024 walkers) but twice as many walkers in flight: C3 +7.5 %, C2 +15 % at
+// 4 096 walkers per GPU (A/B builds on B200).  The launcher picks by the size of the batch.
+template <int NB, int W, bool REPLAY, int MINB>
+__global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
 {
     constexpr int T = 32;
     const WCtx w = setup_ctx_g<32, 1>(a.cfg, W > 1 ? W : 0);

@@ -230,7 +230,7 @@ class WalkerPool:
         self.launches += 1
 
 
-def ffma_peak_tflops(iters: int = 40000) -> float:
+def ffma_peak_tflops(iters: int = 10000) -> float:
     """Measured FP32 FFMA issue peak of the current GPU (roofline denominator in bench.py)."""
     out = C.c_double(0.0)
     check(lib.hans_ffma_peak(int(iters), C.byref(out), _stream()))

@@ -282,6 +282,23 @@ def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     assert not pool.check_overlap().cpu().numpy().any()
 
 
+@pytest.mark.parametrize("shape", ["C1", "C2", "dimer"])
+def test_large_batch_uses_the_register_capped_kernel(eng, oracle, shape):
+    """More walkers than the uncapped warp-per-walker kernel keeps resident (8 per SM): the launcher switches to the
+    128-register build of the same kernel.  Same trajectories, bit for bit."""
+    nw, sweeps, seed = 1800, 1, 31337
+    cfg, H, R, k = make_walkers(shape, nw, seed=17, presweeps=0)
+    pool = make_pool(eng, shape, H, R, k, seed=seed)
+    limit = float(np.median([oracle.volume(H[w]) for w in range(0, nw, 50)]))
+    att, acc = pool.mc_run(sweeps, volume_limit=limit)
+    ctrs = np.zeros(nw, dtype=np.uint64)
+    o_vol, o_att, o_acc = oracle.mc_run_many(cfg, H, R, np.arange(nw), sweeps, limit, seed, np.arange(nw), ctrs)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), o_acc)
+    assert np.array_equal(pool.ctr.cpu().numpy().astype(np.uint64), ctrs)
+    assert_state_equal(pool, H, R)
+    assert np.array_equal(pool.vol.cpu().numpy(), o_vol)
+
+
 @pytest.mark.parametrize("shape,tpw,ws_moves", [("C2", 0, 0), ("C2", 0, 96), ("C1", 0, 64), ("C1", 32, 32), ("C4s", 128, 0),
                                                  ("C4s", 128, 160), ("dimer", 1, 32), ("C4s", 24, 160), ("C1", 28, 64)])
 def test_mc_run_proposals_ahead(eng, oracle, shape, tpw, ws_moves):
