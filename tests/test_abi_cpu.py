@@ -65,8 +65,8 @@ def test_host_side_entry_points_and_validation():
     cfg = _lib.make_cfg(16, 6, [3, 48, 32, 0, 3, 3])
     assert list(cfg.move_cum)[-1] == 1.0 and abs(cfg.move_cum[0] - 3 / 89) < 1e-15
     # f64 master + trial + cell (8 (6N + 3nb + 36)), float4 shadows + filter (16 (2N + nb) + 128), chain radii
-    # (4 nchains), near list (16 + 4 T), ring (64 T)
-    want = ((8 * (6 * 96 + 18 + 36) + 15) // 16 * 16 + 16 * (2 * 96 + 6) + 128 + 4 * 16 + 16 + 4 * 32 + 63) // 64 * 64 + 64 * 32
+    # (4 nchains), near lists (16 + 8 T), ring (64 T)
+    want = ((8 * (6 * 96 + 18 + 36) + 15) // 16 * 16 + 16 * (2 * 96 + 6) + 128 + 4 * 16 + 16 + 8 * 32 + 63) // 64 * 64 + 64 * 32
     assert L.hans_walker_smem_bytes(C.byref(cfg)) == want
     assert L.hans_default_threads_per_walker(C.byref(cfg)) == 32
     big = _lib.make_cfg(128, 6, [1, 384, 256, 384, 3, 3])
