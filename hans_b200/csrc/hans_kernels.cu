@@ -46,39 +46,6 @@ __global__ void shape_delta_kernel(const double *gH, const int32_t *ids, int n, 
     for (int q = 0; q < 9; ++q) dH[(size_t)k * 9 + q] = d[q];
 }
 
-// local MAXLOC (mpihans.py:211-212): ties -> lowest index
-__global__ void argmax_kernel(const double *vol, int n, double *out2)
-{
-    __shared__ double sv[32];
-    __shared__ int si[32];
-    double best = -1.7976931348623157e308;
-    int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double v = vol[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_down_sync(FULL, best, o);
-        const int oi = __shfl_down_sync(FULL, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int nw = (blockDim.x + 31) >> 5;
-        best = threadIdx.x < nw ? sv[threadIdx.x] : -1.7976931348623157e308;
-        bi = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(FULL, best, o);
-            const int oi = __shfl_down_sync(FULL, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (threadIdx.x == 0) { out2[0] = best; out2[1] = (double)bi; }
-    }
-}
-
 // clone (mpihans.py:226-237)
 __global__ void clone_kernel(int N, const double *sH, const double *sR, const double *svol, int src,
                              const int32_t *d_src, double *dH, double *dR, double *dvol, int dst,
@@ -142,6 +109,14 @@ __device__ void block_argmax(const double *vol, int n, double &best, int &bi)
     best = sv[0];
     bi = si[0];
     __syncthreads();
+}
+
+// local MAXLOC (mpihans.py:211-212): ties -> lowest index
+__global__ void argmax_kernel(const double *vol, int n, double *out2)
+{
+    double best; int bi;
+    block_argmax(vol, n, best, bi);
+    if (threadIdx.x == 0) { out2[0] = best; out2[1] = (double)bi; }
 }
 
 // local MAXLOC (mpihans.py:211-212) and staging of the clone source (mpihans.py:226-229)
