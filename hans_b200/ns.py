@@ -16,7 +16,8 @@ choice is needed; the ceiling, iteration counter and active list stay in device 
 
 With HANS_NS_PEER=1 (one node, world > 1) the first three become ONE kernel, hans_ns_exchange_peer:
 records are stored straight into CUDA-IPC-mapped buffers of the other ranks over NVLink and a flag
-per rank and iteration replaces the collective (include/hans_b200.h).  Opt-in: not timed yet.
+per rank and iteration replaces the collective (include/hans_b200.h).  Verified against the NCCL path on two B200s and
+timed at eight (equal: the exchange is ~1 % of a step); NCCL stays the default.
 """
 from __future__ import annotations
 
