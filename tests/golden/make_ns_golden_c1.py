@@ -43,14 +43,19 @@ def main():
     V = np.array([[nap.analyse(r, CFG["K"], DOF, T)["V"] for T in T_GRID] for r in runs])
     Cvp = np.array([[nap.analyse(r, CFG["K"], DOF, T)["Cvp"] for T in T_GRID] for r in runs])
     mode = np.array([[nap.analyse(r, CFG["K"], DOF, T)["mode_i"] for T in T_GRID] for r in runs])
+    # compressibility vs pressure: with E = V the sums are isobaric ones with beta P = 1 / T, so Var(V) = (Cvp - dof/2) T^2 and
+    # the reduced isothermal compressibility is kappa_T P = beta P Var(V) / <V> = (Cvp - dof/2) T / <V> at pressure P* = 1 / T
+    kap = (Cvp - DOF / 2.0) * np.array(T_GRID)[None, :] / V
     out = dict(config=CFG, nseeds=NSEEDS, dof=DOF, checkpoints=idx.tolist(), mean_lnV=lnv[:, idx].mean(0).tolist(),
                se_lnV=(lnv[:, idx].std(0, ddof=1) / np.sqrt(NSEEDS)).tolist(), T_grid=T_GRID,
                V_mean=V.mean(0).tolist(), V_sd=V.std(0, ddof=1).tolist(), Cvp_mean=Cvp.mean(0).tolist(),
                Cvp_sd=Cvp.std(0, ddof=1).tolist(), mode_i_mean=mode.mean(0).tolist(),
+               pressure=[1.0 / T for T in T_GRID], kappaP_mean=kap.mean(0).tolist(), kappaP_sd=kap.std(0, ddof=1).tolist(),
                final_volume_mean=float(runs[:, -1].mean()))
     json.dump(out, open(os.path.join(HERE, "ns_curves_c1.json"), "w"), indent=1)
     print("V(T)", np.round(V.mean(0), 1), "+-", np.round(V.std(0, ddof=1), 1))
     print("Cvp(T)", np.round(Cvp.mean(0), 1), "+-", np.round(Cvp.std(0, ddof=1), 1))
+    print("kappa_T P", np.round(kap.mean(0), 3), "+-", np.round(kap.std(0, ddof=1), 3))
     print("mode iteration", mode.mean(0), "first / last volume", runs[:, 0].mean(), runs[:, -1].mean())
 
 

@@ -315,7 +315,8 @@ def test_ns_level2_c1_shape_vs_oracle_ensemble(eng):
     """16 hexamers, move_ratio 3,48,32,0,3,3, walklength 40, K = 20 (the reference's README run on one rank), 1600
     iterations, 8 independent seeds on the GPU against 8 independent seeds of the CPU oracle's nested sampling
     (tests/golden/ns_curves_c1.json): ln V vs iteration, the final packing fraction, and the <V>(T) and Cvp(T) columns of
-    ns_analyse over the T grid must agree within the stated multiples of the combined standard errors."""
+    ns_analyse over the T grid -- and the compressibility-vs-pressure curve derived from them -- must agree within the
+    stated multiples of the combined standard errors."""
     from hans_b200.mpihans import chunk_end
     from hans_b200.ns import NestedSampler
     from oracle import ns_analyse_port as nap
@@ -358,7 +359,10 @@ def test_ns_level2_c1_shape_vs_oracle_ensemble(eng):
     # ns_analyse columns over the T grid (mpihans.py:311-329 runs it on volumes.txt; E = V, n_Extra_DOF = dof)
     V = np.array([[nap.analyse(r, s["K"], g["dof"], T)["V"] for T in g["T_grid"]] for r in runs])
     Cvp = np.array([[nap.analyse(r, s["K"], g["dof"], T)["Cvp"] for T in g["T_grid"]] for r in runs])
-    for name, mine, ref_mean, ref_sd in (("V", V, g["V_mean"], g["V_sd"]), ("Cvp", Cvp, g["Cvp_mean"], g["Cvp_sd"])):
+    # compressibility vs pressure (P* = 1 / T): kappa_T P = (Cvp - dof / 2) T / <V>
+    kap = (Cvp - g["dof"] / 2.0) * np.array(g["T_grid"])[None, :] / V
+    for name, mine, ref_mean, ref_sd in (("V", V, g["V_mean"], g["V_sd"]), ("Cvp", Cvp, g["Cvp_mean"], g["Cvp_sd"]),
+                                         ("kappaP", kap, g["kappaP_mean"], g["kappaP_sd"])):
         m, sd = mine.mean(0), mine.std(0, ddof=1)
         comb = np.sqrt(sd ** 2 / nseeds + np.array(ref_sd) ** 2 / g["nseeds"])
         zz = (m - np.array(ref_mean)) / comb
