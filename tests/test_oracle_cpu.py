@@ -357,3 +357,51 @@ def test_oracle_reproduces_reference_golden(oracle, shape):
     assert oracle.volume(H) == float(z[shape + ".vol_det"][0])
     scale = max(np.abs(R).max(), np.abs(H).max())
     assert np.abs(R - z[shape + ".R_np"]).max() <= 1e-13 * scale and np.abs(H - z[shape + ".H_np"]).max() <= 1e-13 * scale
+
+
+# ---- the arithmetic shortcuts the oracle shares with the kernels, against the reference's own formulas --------------------
+def test_volume_move_weight_equals_reference_formula(oracle):
+    """The acceptance weight of a volume move is evaluated as (V'/V)^nchains * exp(-P dV) by repeated multiplication
+    (hd_powi); the reference's formula is exp(-P dV + nchains ln(V'/V)) (mirrored at /root/reference/NesSa/MCNS.py:266).
+    They must agree to rounding (<= 1e-13 relative for up to 128 chains), so `u < boltz` (MCNS.py:351) can only differ for
+    u within that distance of the weight."""
+    rng = np.random.default_rng(12)
+    worst = 0.0
+    for nchains in (1, 2, 16, 32, 64, 128):
+        for P in (0.0, 2e-3):
+            cfg = oracle.make_cfg(nchains, 1, [1, 0, 0, 0, 0, 0], pressure=P)
+            L = 6.0 * nchains ** (1 / 3)
+            H0 = np.eye(3) * L
+            R0 = (np.indices((6, 6, 6)).reshape(3, -1).T[:nchains] + 0.5) * (L / 6.0)   # simple cubic: no overlaps
+            V0 = oracle.volume(H0)
+            for _ in range(40):
+                dV = float(rng.uniform(-0.2, 0.3) * V0)
+                p = np.zeros(1, dtype=oracle.PROPOSAL_DTYPE)
+                p["type"], p["p"][0, 0] = oracle.VOL, dV
+                H, R = H0.copy(), R0.copy()
+                dec = oracle.replay(cfg, H, R, p, mode=oracle.MODE_PROPOSE)[0]
+                if dec["boltz"] == 0.0:      # (a shrink that made spheres overlap)
+                    continue
+                want = math.exp(-P * dV + nchains * math.log((V0 + dV) / V0))
+                worst = max(worst, abs(dec["boltz"] - want) / want)
+    assert 0 < worst < 1e-13, worst
+
+
+def test_minimum_image_equals_numpy_statement(oracle):
+    """ho_pair_r2 (H^-1 by cofactors times ONE reciprocal of the determinant, FMA chains) against the plain numpy statement of
+    the same rule (np.linalg.inv, nearest-integer wrap, back through H) on random and sheared cells: equal to 1e-12, so the
+    strict decision r^2 < 1 can only differ for pairs within that distance of contact."""
+    rng = np.random.default_rng(13)
+    worst = 0.0
+    for _ in range(4000):
+        H = np.eye(3) * rng.uniform(3, 15) + rng.normal(scale=1.2, size=(3, 3))
+        if abs(np.linalg.det(H)) < 5:
+            continue
+        ri, rj = rng.uniform(-20, 20, size=3), rng.uniform(-20, 20, size=3)
+        s = (rj - ri) @ np.linalg.inv(H)
+        s -= np.rint(s)
+        m = s @ H
+        want = float(m @ m)
+        got = oracle.pair_r2(H, ri, rj)
+        worst = max(worst, abs(got - want) / max(want, 1e-3))
+    assert worst < 1e-12, worst
