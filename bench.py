@@ -516,9 +516,10 @@ def run_b200(args):
             "config": {"workload": workload_string(name, nw), "total_walkers": nw * world, "moves_per_iteration": moves_per_step,
                        "initial_walk_sweeps": args.initial_walk, "parallel_mode": "every resident walker walks each iteration",
                        "threads_per_walker": args.tpw or "default", "volume_first_last": [vol_first, vol_last],
-                       "cache": "working set (walker state) lives in shared memory for the whole walk; the proposal stream "
-                                f"read per launch ({64.0 * nw * WALKLENGTH * mps / 1e6:.0f} MB) is written by the generator "
-                                "kernel right before it; no L2 flush needed"},
+                       "cache": "inputs larger than L2: every step streams a fresh proposal buffer of "
+                                f"{64.0 * nw * WALKLENGTH * mps / 1e6:.0f} MB (written by the generator kernel, read once by the walk "
+                                "kernel; L2 is 126 MB) -- no flush needed; the walker state itself lives in shared memory for the "
+                                "whole walk"},
             "ns_iterations_per_s": args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "moves/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "dropin_mc_run_batch": dropin},
