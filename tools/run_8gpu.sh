@@ -10,7 +10,7 @@ run() { # name nproc extra-env args...
         bench.py --gpus "$n" --steps 20 --warmup 5 --no-cpu --no-dropin "$@" > "gpurun_out/$name.json" 2> "gpurun_out/$name.err"
     echo "$name rc=$? $(head -c 300 gpurun_out/$name.json)"
 }
-run r02_bench_c3_n8_nccl 8 HANS_NS_PEER=0 --others C4,C5
-run r02_bench_c3_n8_peer 8 HANS_NS_PEER=1 --others ""
-run r02_bench_c3_strong_n4 4 HANS_NS_PEER=0 --total-walkers 8192 --others ""
-run r02_bench_c3_strong_n2 2 HANS_NS_PEER=0 --total-walkers 8192 --others ""
+run r02b_bench_c3_n8_nccl 8 HANS_NS_PEER=0 --others C4,C5
+run r02b_bench_c3_n8_peer 8 HANS_NS_PEER=1 --others ""
+run r02b_bench_c3_strong_n4 4 HANS_NS_PEER=0 --total-walkers 8192 --others ""
+run r02b_bench_c3_strong_n2 2 HANS_NS_PEER=0 --total-walkers 8192 --others ""
