@@ -767,6 +767,15 @@ static WsPlan ws_plan(int n_active, int total, bool have_ws, uint64_t workspace_
     return p;
 }
 
+int hans_walk_kernel_launches(const hans_cfg *cfg, int threads_per_walker)
+{
+    if (!cfg || check_cfg(cfg) != HANS_OK) return 1;
+    if (threads_per_walker != 0 || rho_split() <= 0.0 || lean_applies(cfg) || !box_cells_can_pay(cfg)) return 1;
+    if (hans_default_team(cfg)) return 2; // the plain and the cell-list build of the warp-per-move kernel (launch_side)
+    const int T = pick_T(cfg, 0);
+    return (cta_smem_bytes(cfg, T) <= SMEM_MAX && cells_fit(cfg, T, 2)) ? 2 : 1;
+}
+
 int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes)
 {
     const WsPlan p = ws_plan(n_active, nmoves, have_workspace != 0, workspace_bytes);

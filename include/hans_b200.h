@@ -163,8 +163,11 @@ int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t
                          double *d_vol, uint64_t *d_pair_tests, int threads_per_walker,
                          void *d_workspace, uint64_t workspace_bytes, void *stream);
 
-/* kernel launches hans_mc_run_batch_ws makes for a walk of nmoves moves per walker (for launch accounting) */
+/* kernel launches hans_mc_run_batch_ws makes for a walk of nmoves moves per walker (for launch accounting), counting ONE
+ * walk kernel per chunk; hans_walk_kernel_launches tells how many walk kernels a chunk really launches for a shape: 2 when
+ * the default dispatch launches the plain and the cell-list build side by side (long chains, see HANS_TPW_CELLS), else 1 */
 int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes);
+int hans_walk_kernel_launches(const hans_cfg *cfg, int threads_per_walker);
 
 /* d_props[k][m] = proposal number d_ctr[walker k] + m of walker k = d_ids[k], m < nmoves: exactly
  * the proposals hans_mc_run_batch would draw (four Philox4x32-10 blocks per move
