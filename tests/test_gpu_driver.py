@@ -225,3 +225,38 @@ initial_config = start.extxyz
     bad = dict(NSio.parse_hans_text(text.replace("nchains = 6", "nchains = 5").replace("directory = imp", "directory = imp2")))
     with pytest.raises(AssertionError):
         mpihans.main(bad)
+
+
+def test_driver_meets_the_reference_file_contract(tmp_path, monkeypatch):
+    """The same input the unmodified reference driver was run on in the build container
+    (tests/test_reference_driver_live_cpu.py -> tests/golden/ref_driver_contract.json), through hans_b200.mpihans on the
+    B200: same files, same volumes.txt header and line format, same restart attributes (names and types), group names
+    and datasets, same trajectory cadence."""
+    import json
+    import re
+    from hans_b200 import NSio, mpihans
+    from hans_b200.atoms import read_extxyz
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_driver_contract.json")))
+    monkeypatch.chdir(tmp_path)
+    mpihans.main(dict(NSio.parse_hans_text(g["input"] + "seed = 3\n")))
+    os.chdir(tmp_path)
+    assert set(g["files"]) <= set(os.listdir("run1"))
+    text = open("run1/volumes.txt").read()
+    lines = text.split("\n")
+    assert lines[0] == g["volumes_header"] and (lines[-1] == "") == g["trailing_newline"]
+    body = [l for l in lines[1:] if l]
+    assert len(body) == g["n_volume_lines"] and all(re.match(g["volumes_line_regex"], l) for l in body)
+    assert [int(l.split()[0]) for l in body] == list(range(g["n_volume_lines"]))
+    frames = read_extxyz("run1/traj.extxyz", ":")
+    assert len(frames) == g["traj_frames"]
+    attrs, walkers = NSio.open_restart("run1/restart.hdf5")
+    assert sorted(walkers) == g["restart_groups"]
+
+    def kind(v):
+        a = np.asarray(v)
+        return ("str" if a.dtype.kind in "US" else "int" if a.dtype.kind in "iu" else "float" if a.dtype.kind == "f" else a.dtype.kind) + \
+               ("" if a.shape == () else str(list(a.shape)))
+    for k, t in g["restart_attrs"].items():
+        assert k in attrs and kind(attrs[k]) == t, (k, t, attrs.get(k))
+    c, u, ctr = walkers["walker_0_0001"]
+    assert list(c.shape) == g["restart_datasets"]["coordinates"] and list(u.shape) == g["restart_datasets"]["unitcell"]
