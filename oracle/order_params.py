@@ -4,7 +4,8 @@ Q = mean(1.5 u u^T - 0.5 I), largest eigenvalue) and trans_order_param :30-55 wi
 (fractional mean over beads a0:a1, i.e. WITHOUT the last bead; the bead itself for Nbeads = 1).  The reference's
 trans_order_param indexes r[i] for i < Nchains*Nbeads although r has Nchains entries (IndexError for Nbeads > 1);
 the restatement sums over the Nchains centres, which is what it computes when it runs (Nbeads = 1).
-Parity: pinned against the reference's own formulas only (the reference has no tests; ase is not installed)."""
+Parity: pinned by executing the unmodified /root/reference/nematic.py with an ase stand-in on the same configurations
+(tests/test_reference_live_cpu.py::test_reference_nematic_functions_match_the_numpy_restatement, 1e-12)."""
 import numpy as np
 
 

@@ -357,3 +357,69 @@ def test_committed_golden_vectors_are_current(tmp_path):
     for k in old_npz:
         assert np.array_equal(old_npz[k], new_npz[k]), k
     assert json.load(open(tmp_path / "ref_live_trace.json")) == old_tr
+
+
+def test_reference_nematic_functions_match_the_numpy_restatement():
+    """/root/reference/nematic.py imported unmodified (ase.io and matplotlib replaced by empty stand-ins; the Atoms stand-in
+    supplies what ase would: scaled positions wrapped into [0, 1), minimum-image end-to-end vectors, the cell volume): its
+    nematic_order_param (nematic.py:83-137) and trans_order_param (nematic.py:30-55; runs for Nbeads = 1 only, see
+    oracle/order_params.py) against the restatement the GPU kernel is checked with (hans_order_params, tests/test_gpu_ns.py)."""
+    import importlib.util
+    import os
+    import types
+    from oracle import order_params as op
+
+    class Cell(np.ndarray):
+        def reciprocal(self):
+            return np.linalg.inv(np.asarray(self)).T
+
+    class At:
+        def __init__(self, cell, pos):
+            self.cell = np.asarray(cell).view(Cell)
+            self.pos = np.asarray(pos)
+
+        def get_volume(self): return float(abs(np.linalg.det(np.asarray(self.cell))))
+        def get_positions(self): return self.pos.copy()
+        def get_scaled_positions(self): return (self.pos @ np.linalg.inv(np.asarray(self.cell))) % 1.0
+
+        def get_distance(self, a0, a1, mic=False, vector=False):
+            d = self.pos[a1] - self.pos[a0]
+            if mic:   # nearest image (what ase's find_mic returns): wrap, then brute force over the 27 neighbouring cells
+                c = np.asarray(self.cell)
+                f = d @ np.linalg.inv(c)
+                d = (f - np.rint(f)) @ c
+                cands = [d + np.array([i, j, k]) @ c for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)]
+                d = min(cands, key=lambda v: float(v @ v))
+            return d if vector else float(np.linalg.norm(d))
+
+    saved = {k: sys.modules.get(k) for k in ("ase", "ase.io", "matplotlib", "matplotlib.pyplot")}
+    try:
+        ase = types.ModuleType("ase"); ase.io = types.ModuleType("ase.io")
+        mpl = types.ModuleType("matplotlib"); mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+        sys.modules.update({"ase": ase, "ase.io": ase.io, "matplotlib": mpl, "matplotlib.pyplot": mpl.pyplot})
+        spec = importlib.util.spec_from_file_location("_hans_reference_nematic", os.path.join(ref_live.REFERENCE_ROOT, "nematic.py"))
+        nem = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(nem)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(4)
+    for shape, seed in (("C1", 3), ("dimer", 4), ("p7", 5), ("C2", 6)):
+        nchains, nbeads, mr = SHAPES[shape]
+        cfg = ho.make_cfg(nchains, nbeads, mr)
+        H, R = ho.grow_walkers(cfg, 4, seed)
+        for w in range(4):   # sheared cells, beads pushed out of the cell by lattice vectors
+            ho.change_box(cfg, H[w], R[w], rng.normal(scale=0.6, size=(3, 3)))
+            R[w] += rng.integers(-2, 3, size=(R.shape[1], 1)) * H[w][rng.integers(3)]
+        configs = [At(H[w], R[w]) for w in range(4)]
+        if nbeads > 1:
+            want = nem.nematic_order_param(configs, nbeads, nchains)
+            got = op.nematic_order_param(H, R, nbeads, nchains)
+            assert np.allclose(got, np.real(want), rtol=0, atol=1e-12), (shape, got, want)
+        else:
+            want = nem.trans_order_param(configs, nbeads, nchains)
+            got = op.trans_order_param(H, R, nbeads, nchains)
+            assert np.allclose(got, want, rtol=0, atol=1e-12), (shape, got, want)
