@@ -59,7 +59,7 @@ class NsArgs(C.Structure):
 EXPORTS = [
     "hans_abi_version", "hans_last_error", "hans_device_count", "hans_walker_smem_bytes",
     "hans_moves_per_sweep", "hans_default_threads_per_walker", "hans_default_window", "hans_default_team", "hans_mc_run_batch",
-    "hans_mc_run_batch_ws", "hans_mc_run_launches", "hans_walk_kernel_launches", "hans_gen_proposals",
+    "hans_mc_run_batch_ws", "hans_mc_run_launches", "hans_gen_proposals",
     "hans_replay",
     "hans_check_overlap", "hans_cell_metrics", "hans_change_box", "hans_shape_delta", "hans_grow", "hans_grow_chain",
     "hans_argmax", "hans_clone", "hans_ns_pack", "hans_ns_resolve", "hans_ns_peer_bytes", "hans_peer_alloc",
@@ -110,7 +110,6 @@ def _load():
     L.hans_default_window.argtypes = [cp]; L.hans_default_window.restype = C.c_int
     L.hans_default_team.argtypes = [cp]; L.hans_default_team.restype = C.c_int
     L.hans_mc_run_launches.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64]; L.hans_mc_run_launches.restype = C.c_int
-    L.hans_walk_kernel_launches.argtypes = [cp, C.c_int]; L.hans_walk_kernel_launches.restype = C.c_int
     L.hans_mc_run_batch.argtypes = [cp, vp, vp, vp, vp, i32, i32, vp, f64, u64, u32, vp, vp, vp, vp, i32, vp]
     L.hans_mc_run_batch_ws.argtypes = [cp, vp, vp, vp, vp, i32, i32, vp, f64, u64, u32, vp, vp, vp, vp, i32, vp, u64, vp]
     L.hans_gen_proposals.argtypes = [cp, vp, vp, i32, i32, u64, u32, vp, vp]

@@ -367,12 +367,11 @@ static int check_cfg(const hans_cfg *c)
     return HANS_OK;
 }
 
-static size_t cta_smem_bytes(const hans_cfg *c, int T, int cells_mode = 0)
+static size_t cta_smem_bytes(const hans_cfg *c, int T, bool cells = false)
 {
     const int gpc = (T == 32) ? 4 : 1;
     const int N = c->nchains * c->nbeads;
-    return (walker_smem_bytes(N, c->nbeads, T) + (cells_mode ? cell_smem_bytes(N, cells_mode == 2) : 0)) * gpc +
-           cta_extra_bytes(c->nbeads, c->nexclude);
+    return (walker_smem_bytes(N, c->nbeads, T) + (cells ? cell_smem_bytes(N) : 0)) * gpc + cta_extra_bytes(c->nbeads, c->nexclude);
 }
 
 static int sm_count()
@@ -489,10 +488,10 @@ static int pick_W(const hans_cfg *c, int tpw)
 
 // One CTA of NWARP warps per walker, one warp per move of a speculative window (hans_team.cuh): chains only
 // (the pruning works on chain bounding spheres), and the walker plus NWARP trial chains must fit shared memory.
-static size_t team_smem_bytes(const hans_cfg *c, int nwarp, bool box_cells = false)
+static size_t team_smem_bytes(const hans_cfg *c, int nwarp)
 {
     return walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp) +
-           team_tail_bytes(nwarp) + (box_cells ? cell_smem_bytes(c->nchains * c->nbeads, true) : 0) + cta_extra_bytes(c->nbeads, c->nexclude);
+           team_tail_bytes(nwarp) + cta_extra_bytes(c->nbeads, c->nexclude);
 }
 static bool team_applies(const hans_cfg *c, int nwarp)
 {
@@ -503,21 +502,14 @@ template <bool REPLAY> static int launch_team(WalkArgs a, int nwarp, cudaStream_
 {
     const hans_cfg *c = &a.cfg;
     a.team_res = (int)((walker_smem_bytes(c->nchains * c->nbeads, c->nbeads, 32 * nwarp) + window_smem_bytes(c->nbeads, nwarp)) / 4);
-    if (a.cells_mode == 2 && team_smem_bytes(c, nwarp, true) > 227 * 1024) a.cells_mode = 0;
-    const size_t smem = team_smem_bytes(c, nwarp, a.cells_mode == 2);
+    const size_t smem = team_smem_bytes(c, nwarp);
     const int cap = sm_count() * 8, grid = a.n_active < cap ? a.n_active : cap;
     int rc = HANS_OK;
-#define TEAM_LAUNCH(NN, WW)                                                                 \
-    {                                                                                       \
-        if (a.cells_mode == 2) {                                                            \
-            rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY, true>, smem);                 \
-            if (rc) return rc;                                                              \
-            walk_team_kernel<NN, WW, REPLAY, true><<<grid, 32 * WW, smem, st>>>(a);         \
-        } else {                                                                            \
-            rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY, false>, smem);                \
-            if (rc) return rc;                                                              \
-            walk_team_kernel<NN, WW, REPLAY, false><<<grid, 32 * WW, smem, st>>>(a);        \
-        }                                                                                   \
+#define TEAM_LAUNCH(NN, WW)                                                        \
+    {                                                                              \
+        rc = prep_kernel(walk_team_kernel<NN, WW, REPLAY>, smem);                  \
+        if (rc) return rc;                                                         \
+        walk_team_kernel<NN, WW, REPLAY><<<grid, 32 * WW, smem, st>>>(a);          \
     }
 #define TEAM_NB(WW)                                                                \
     switch (c->nbeads) {                                                           \
@@ -597,19 +589,6 @@ int hans_default_team(const hans_cfg *cfg)
     return 0;
 }
 
-// Bead number density of a trial configuration above which a box move is tested through the cell list instead of the
-// chain-pair pass when threads_per_walker = 0 (measured crossover, profiles/r02_cells_*; HANS_RHO_SPLIT overrides it for
-// measurements, 0 switches the cell list off)
-static double rho_split()
-{
-    static double v = -1.0;
-    if (v < 0.0) {
-        const char *e = getenv("HANS_RHO_SPLIT");
-        v = e ? atof(e) : 0.35;
-    }
-    return v;
-}
-
 // threads per walker of the cell-list kernel for a shape
 static int cells_T(const hans_cfg *c)
 {
@@ -624,7 +603,7 @@ static int cells_T(const hans_cfg *c)
 static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory, int T, cudaStream_t st)
 {
     int rc = HANS_OK;
-    const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode);
+    const size_t smem = cta_smem_bytes(cfg, T, a.cells_mode != 0);
     if (smem > SMEM_MAX) { // state in global memory
         BigState b;
         rc = big_alloc(b, smem, (a.n_active + (T == 32 ? 3 : 0)) / (T == 32 ? 4 : 1), st);
@@ -653,21 +632,8 @@ static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory,
     return HANS_OK;
 }
 
-// Can a box move of this shape ever take the cell-list branch of move_box?  It needs the reach of a pair of chains
-// (two bounding radii of a zig-zag chain + sigma) to exceed half the cell width at a bead density a hard-sphere chain
-// fluid can reach; shapes that cannot (short chains: C5's hexamers would need rho = 3.7) keep the kernels without the
-// list code (instruction-cache footprint).
-static bool box_cells_can_pay(const hans_cfg *c)
-{
-    const int N = c->nchains * c->nbeads;
-    if (N < 192 || c->nbeads < 2) return false;
-    const double reach = 2.0 * 0.82 * c->bondlength * (double)(c->nbeads >> 1) + 1.0;
-    const double rho_crit = (double)N / ((2.0 * reach) * (2.0 * reach) * (2.0 * reach));
-    return rho_crit < 1.0;
-}
-
 // does the cell-list kernel fit shared memory for this shape (with T threads per walker)?
-static bool cells_fit(const hans_cfg *cfg, int T, int mode = 1) { return cta_smem_bytes(cfg, T, mode) <= 227 * 1024; }
+static bool cells_fit(const hans_cfg *cfg, int T) { return cta_smem_bytes(cfg, T, true) <= 227 * 1024; }
 
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
 {
@@ -687,19 +653,6 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         const int nwarp = threads_per_walker - 20;
         if (!team_applies(cfg, nwarp))
             return fail(HANS_ELIMIT, "the warp-per-move kernel (threads_per_walker 24, 28) needs chains (nbeads > 1) that fit shared memory");
-        if (dflt && rho_split() > 0.0 && box_cells_can_pay(cfg)) {
-            // default for large chain systems with long chains: box moves of DENSE trial configurations (where bounding
-            // spheres prune nothing and the chain-pair pass degenerates to all pairs) go through a cell list of the trial
-            // configuration.  The kernel that carries that code is 10 % slower on dilute walkers (code size), so the walk
-            // is launched as both kernels and the ceiling decides which one runs (WalkArgs::launch_side).
-            WalkArgs lo = a, hi = a;
-            lo.launch_side = 1; hi.launch_side = 2;
-            lo.rho_split = hi.rho_split = rho_split();
-            hi.cells_mode = 2;
-            int rc = from_memory ? launch_team<true>(lo, nwarp, st) : launch_team<false>(lo, nwarp, st);
-            if (rc) return rc;
-            return from_memory ? launch_team<true>(hi, nwarp, st) : launch_team<false>(hi, nwarp, st);
-        }
         return from_memory ? launch_team<true>(a, nwarp, st) : launch_team<false>(a, nwarp, st);
     }
     if (threads_per_walker < 24 && a.mode == HANS_MODE_FUSED) { // PROPOSE leaves trial states: cooperative kernel
@@ -715,15 +668,6 @@ static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int t
         // test (all pairs of thousands of beads is what the list is for)
         a.cells_mode = 1;
         return launch_coop(cfg, a, from_memory, 256, st);
-    }
-    if (dflt && box_cells_can_pay(cfg) && cells_fit(cfg, T, 2) && rho_split() > 0.0) {
-        WalkArgs lo = a, hi = a; // (as for the warp-per-move kernel above)
-        lo.launch_side = 1; hi.launch_side = 2;
-        lo.rho_split = hi.rho_split = rho_split();
-        hi.cells_mode = 2;
-        const int rc = launch_coop(cfg, lo, from_memory, T, st);
-        if (rc) return rc;
-        return launch_coop(cfg, hi, from_memory, T, st);
     }
     return launch_coop(cfg, a, from_memory, T, st);
 }
@@ -765,15 +709,6 @@ static WsPlan ws_plan(int n_active, int total, bool have_ws, uint64_t workspace_
     p.chunk = chunk >= (uint64_t)total ? total : (int)(chunk & ~(uint64_t)31); // a multiple of 32: the kernels take proposals 32 at a time
     p.nchunks = p.chunk ? (total + p.chunk - 1) / p.chunk : 0;
     return p;
-}
-
-int hans_walk_kernel_launches(const hans_cfg *cfg, int threads_per_walker)
-{
-    if (!cfg || check_cfg(cfg) != HANS_OK) return 1;
-    if (threads_per_walker != 0 || rho_split() <= 0.0 || lean_applies(cfg) || !box_cells_can_pay(cfg)) return 1;
-    if (hans_default_team(cfg)) return 2; // the plain and the cell-list build of the warp-per-move kernel (launch_side)
-    const int T = pick_T(cfg, 0);
-    return (cta_smem_bytes(cfg, T) <= SMEM_MAX && cells_fit(cfg, T, 2)) ? 2 : 1;
 }
 
 int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes)

@@ -210,16 +210,12 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
     return __reduce_or_sync(FULL, (ov ? 1u : 0u) | (amb ? 2u : 0u) | (oldb << 8) | (newb << 16));
 }
 
-template <int NB, int NWARP, bool REPLAY, bool CL>
+template <int NB, int NWARP, bool REPLAY>
 __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const WalkArgs a)
 {
     constexpr int T = 32 * NWARP;
     static_assert(NWARP >= 2 && NWARP <= 8, "result words carry 8 bits per earlier move");
-    if (wrong_side(a)) return;
-    WCtx w = setup_ctx_g<T, 1>(a.cfg, NWARP, team_tail_bytes(NWARP) + ((CL && a.cells_mode == 2) ? (int)cell_smem_bytes(a.cfg.nchains * a.cfg.nbeads, true) : 0),
-                               team_tail_bytes(NWARP));
-    w.cells = (CL && a.cells_mode == 2) ? 2 : 0; // box moves through a cell list of the trial configuration when it is dense
-    w.rho_box = (float)a.rho_split;
+    const WCtx w = setup_ctx_g<T, 1>(a.cfg, NWARP, team_tail_bytes(NWARP));
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const int nb = NB ? NB : w.nb;
     unsigned *res = reinterpret_cast<unsigned *>(smem) + a.team_res; // (walker + window area) / 4, from the launcher
@@ -297,7 +293,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                         const Dec d = move_chain<T>(w, ring + q, HANS_MODE_FUSED, pairs);
                         accepted = d.accepted; reason = d.reason; boltz = d.boltz;
                     } else {
-                        const DecP d = move_box<T, CL>(w, q, limit, HANS_MODE_FUSED);
+                        const DecP d = move_box<T>(w, q, limit, HANS_MODE_FUSED);
                         accepted = d.accepted; reason = d.reason; boltz = d.boltz; pairs += d.pairs;
                         f = load_filt(W_SF(w)); // the cell may have changed (also on a reverted shear / stretch)
                     }

@@ -189,9 +189,7 @@ class WalkerPool:
                                        _ptr(att), _ptr(acc), self.vol.data_ptr(),
                                        self.pair_tests.data_ptr() if count_pairs else None, self.tpw,
                                        _ptr(self._ws) if ws_bytes else None, int(ws_bytes), _stream()))
-        nl = lib.hans_mc_run_launches(n, nmoves, 1 if ws_bytes else 0, int(ws_bytes))  # (generate + walk) per chunk
-        extra = lib.hans_walk_kernel_launches(C.byref(c), self.tpw) - 1               # a second walk kernel per chunk
-        self.launches += nl + extra * (nl // 2 if ws_bytes else nl)
+        self.launches += lib.hans_mc_run_launches(n, nmoves, 1 if ws_bytes else 0, int(ws_bytes))  # (generate + walk) per chunk
         return att, acc
 
     def replay(self, ids, proposals: np.ndarray, volume_limit: float = DBL_MAX, mode: int = MODE_FUSED) -> np.ndarray:

@@ -59,9 +59,9 @@ enum {
 /* OR-ed into threads_per_walker (0, 32, 64, 128, 256): the cooperative kernel with the PER-WALKER CELL LIST -- bins in
  * fractional space at least 1.001 sigma wide in every direction, overlap candidates of a bead = the beads of the <= 27
  * bins around it (the role of hs_alkane's link cells, bypassed by the reference at MCNS.py:603).  Same decisions and
- * trajectories as every other kernel, bit for bit.  With threads_per_walker = 0 the library uses a cell list of the TRIAL
- * configuration by itself for the box moves of walkers of 192 beads and more once bounding spheres prune nothing (the
- * reach of a pair of chains exceeds half the smallest cell width) and the bead density exceeds the measured crossover. */
+ * trajectories as every other kernel, bit for bit.  With threads_per_walker = 0 the library uses it by itself for walkers
+ * that do not fit shared memory (state in global memory); for the BASELINE shapes the sphere-pruning kernels measured faster
+ * at every density, so it stays an explicit choice there. */
 #define HANS_TPW_CELLS 4096
 
 /* Model + move parameters.  Replaces hs_alkane's module state set through
@@ -139,8 +139,8 @@ int hans_default_team(const hans_cfg *cfg);
  *                     and trajectory, bit for bit); box moves are shared by the whole CTA;
  *                     any of 0, 32, 64, 128, 256 | HANS_TPW_CELLS: cooperative kernel with the per-walker cell list;
  *                     0 = the measured default per shape: hans_default_window if non-zero, else
- *                     hans_default_team if non-zero, else hans_default_threads_per_walker -- and, for walkers of 192
- *                     beads and more, box moves of dense trial configurations through a cell list.
+ *                     hans_default_team if non-zero, else hans_default_threads_per_walker (walkers beyond shared memory:
+ *                     state in global memory + the cell list).
  *                     Every variant produces the same trajectory; the choice is speed only.
  * Replaces: the Python loop MCNS.py:304-383 and every alk.* call inside it. */
 int hans_mc_run_batch(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t *d_ctr,
@@ -163,11 +163,8 @@ int hans_mc_run_batch_ws(const hans_cfg *cfg, double *d_H, double *d_R, uint64_t
                          double *d_vol, uint64_t *d_pair_tests, int threads_per_walker,
                          void *d_workspace, uint64_t workspace_bytes, void *stream);
 
-/* kernel launches hans_mc_run_batch_ws makes for a walk of nmoves moves per walker (for launch accounting), counting ONE
- * walk kernel per chunk; hans_walk_kernel_launches tells how many walk kernels a chunk really launches for a shape: 2 when
- * the default dispatch launches the plain and the cell-list build side by side (long chains, see HANS_TPW_CELLS), else 1 */
+/* kernel launches hans_mc_run_batch_ws makes for a walk of nmoves moves per walker (for launch accounting) */
 int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes);
-int hans_walk_kernel_launches(const hans_cfg *cfg, int threads_per_walker);
 
 /* d_props[k][m] = proposal number d_ctr[walker k] + m of walker k = d_ids[k], m < nmoves: exactly
  * the proposals hans_mc_run_batch would draw (four Philox4x32-10 blocks per move

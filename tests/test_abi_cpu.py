@@ -157,12 +157,6 @@ def test_workspace_plan_launch_count():
     assert L.hans_mc_run_launches(1024, 2840, 1, 1000 * per_move) == 2 * 3    # 992 moves fit: generate, walk, three times
     assert L.hans_mc_run_launches(1024, 2840, 0, 0) == 1                       # no workspace: generation inside the walk kernel
     assert L.hans_mc_run_launches(8, 87, 1, 8 * 64 * 40) == 2 * 3              # 32 of 87 moves fit
-    # walk kernels per chunk: 2 where the default dispatch launches the plain and the cell-list build side by side
-    # (long chains: a pair of chains can out-reach half the cell at a reachable density), else 1
-    wl = lambda nc, nb, tpw=0: L.hans_walk_kernel_launches(C.byref(_lib.make_cfg(nc, nb, [1, 1, 1, 1, 1, 1])), tpw)
-    assert wl(16, 6) == 1 and wl(64, 1) == 1 and wl(128, 6) == 1               # C3, C2 (warp per walker), C5 (hexamers)
-    assert wl(32, 12) == 2 and wl(24, 16) == 2 and wl(14, 16) == 2             # C4 and other long-chain shapes
-    assert wl(32, 12, 24) == 1 and wl(32, 12, 128) == 1                        # an explicit kernel choice is one launch
 
 
 def test_peer_exchange_buffer_size():

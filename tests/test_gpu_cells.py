@@ -166,10 +166,9 @@ def test_cells_mc_run_trajectory_bit_exact(eng, oracle, shape, T, sweeps, densit
 @pytest.mark.parametrize("shape,density,ceiling", [("C4", 0.5, True), ("C4", 0.5, False), ("L16", 0.45, True), ("p16", 0.45, True),
                                                    ("C5", 0.3, True), ("d140", 0.3, True)])
 def test_default_dispatch_dense_walkers(eng, oracle, shape, density, ceiling):
-    """threads_per_walker = 0 on large chain systems.  Long chains (C4's 12-mers, 16-mers) under a ceiling that makes every
-    walker dense: the walk is launched as two kernels and the one whose box moves go through a cell list of the trial
-    configuration runs (WalkArgs::launch_side); without a ceiling, or for short chains (C5, dimers: bounding spheres keep
-    pruning), the plain kernel runs.  Either way the result is the oracle's, and every walker is walked exactly once."""
+    """threads_per_walker = 0 on large chain systems compressed until bounding spheres of chains prune nothing in box moves
+    (long chains: C4's 12-mers, 16-mers) and on short chains (C5, dimers), with and without a ceiling: the default kernels
+    -- warp-per-move and cooperative, whose box moves prune on bead level (lst2 in move_box) -- give the oracle's result."""
     SHAPES["L16"] = (24, 16, [3, 24, 24, 12, 3, 3])    # warp-per-move kernel (>= 24 chains)
     SHAPES["p16"] = (14, 16, [3, 14, 14, 8, 3, 3])     # 224 beads, 14 chains: cooperative kernel
     try:

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Density ladder: moves/s of the walk kernels on C4 / C5 sized walkers from the dilute start to the dense regime
-(which kernel should take a walker at which bead density -> rho_split in hans_kernels.cu)."""
+(which kernel should take a walker at which bead density; the ladders behind profiles/r02_cells_probe.md)."""
 import json
 import os
 import sys
