@@ -195,7 +195,7 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
         const int k = e / NB, b = e - k * NB;
         int b0;
         bool intra;
-        make_trial(w, ring + k, b, NB, w.wc + 3 * NB * k, w.w4 + NB * k, b0, intra);
+        make_trial<false>(w, ring + k, b, NB, w.wc + 3 * NB * k, w.w4 + NB * k, b0, intra);
     }
     const int myck = lane < nw ? ring[lane].ichain : -1; // lane k remembers the chain of move k
     __syncwarp();
