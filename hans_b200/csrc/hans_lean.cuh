@@ -141,7 +141,7 @@ __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr
     bool intra = false;
     make_trial(w, p, w.lane, 32, cn, c4, b0, intra); // (proposal validated by the caller)
     __syncwarp();
-    const float Rt = intra ? chain_radius(cn, NB) : SMF[w.rad + ichain]; // translations and rotations are rigid
+    const float Rt = intra ? chain_radius_warp(cn, NB) : SMF[w.rad + ichain]; // translations and rotations are rigid
     const bool overlap = chain_overlaps_pruned<32, NB>(w, cr.f, ichain, b0, intra, Rt, pairs);
     if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
         const int P = W_P(w) + 3 * c0;

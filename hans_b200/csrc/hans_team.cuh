@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     ichain = meta[q + wid] & 0xffff;
                     make_trial(w, ring + q + wid, ln, 32, cnk, c4k, b0, intra);
                     __syncwarp();
-                    Rt = intra ? chain_radius(cnk, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
+                    Rt = intra ? chain_radius_warp(cnk, nb) : SMF[w.rad + ichain]; // translations and rotations are rigid
                     if (ln == 0) rtw[wid] = Rt;
                 }
                 // ---- A2: warp k tests it (one barrier inside, before the other warps' trial chains are read) ----
