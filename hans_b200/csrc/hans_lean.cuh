@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
                     slot->u_acc = pr.u_acc;
                     my_type = pr.type;
                 }
+                prep_slot(slot);
                 my_plain = (my_type == HANS_TRANS || (NB > 1 && my_type == HANS_ROT) ||
                             (my_type == HANS_DIH && NB >= 4 && slot->idx0 >= 3 && slot->idx0 <= NB - 1)) &&
                            (unsigned)slot->ichain < (unsigned)w.nc;

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                     slot->u_acc = pr.u_acc;
                     my_type = pr.type;
                 }
+                prep_slot(slot);
                 // a single-chain move with a well-formed proposal
                 const bool plain = (my_type == HANS_TRANS || my_type == HANS_ROT ||
                                     (my_type == HANS_DIH && nb >= 4 && slot->idx0 >= 3 && slot->idx0 <= nb - 1)) &&
