@@ -85,7 +85,7 @@ __device__ __forceinline__ double det3(const double *H)
     return (H[0] * c00 + H[1] * c01) + H[2] * c02;
 }
 
-__device__ __noinline__ void hinv(const double *H, double *Hi)
+__device__ __forceinline__ void hinv(const double *H, double *Hi) // inline: the matrices stay in registers
 {
     const double c00 = H[4] * H[8] - H[5] * H[7];
     const double c01 = H[5] * H[6] - H[3] * H[8];
