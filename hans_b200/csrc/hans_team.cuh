@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
     const int nb = NB ? NB : w.nb;
     unsigned *res = reinterpret_cast<unsigned *>(smem) + a.team_res; // (walker + window area) / 4, from the launcher
     float *rtw = reinterpret_cast<float *>(res) + 24;
+    unsigned *cnt = res + 8; // 12 counters in shared memory: twelve registers less in a kernel held at 128
     int *meta = reinterpret_cast<int *>(res) + 32, *info = meta + T + 8;
     int *lst = reinterpret_cast<int *>(res) + 48 + 2 * T + TEAM_LIST * wid; // this warp's near list
     float4 *buf = reinterpret_cast<float4 *>(res + 48 + 2 * T + TEAM_LIST * NWARP) + 32 * wid;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
         load_walker<T>(w, a.H, a.R, wi, true);
         Filt f = load_filt(W_SF(w));
         const unsigned long long ctr0 = REPLAY ? 0ull : a.ctr[wi];
-        unsigned att[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
+        if (threadIdx.x < 12) cnt[threadIdx.x] = 0u; // attempted / accepted per move type (ordered by the first barrier of a batch)
         unsigned pairs = 0;
         unsigned long long pairs_total = 0;
         PropRec *ring = W_RING(w);
@@ -381,8 +382,10 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
             pairs_total += pairs;
             pairs = 0;
             if (my_type >= 0) {
-#pragma unroll
-                for (int t = 0; t < 6; ++t) { att[t] += (my_type == t); acc[t] += (my_type == t && my_acc); }
+                if (my_type < 6) {
+                    atomicAdd(cnt + my_type, 1u);
+                    if (my_acc) atomicAdd(cnt + 6 + my_type, 1u);
+                }
                 if (REPLAY && a.out) {
                     hans_decision *o = a.out + (size_t)k * a.nmoves + m0 + w.lane;
                     o->accepted = my_acc; o->reason = my_reason; o->boltz = my_boltz;
@@ -391,19 +394,9 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
             __syncthreads(); // the ring, meta and info are rewritten by the next batch
         }
         store_walker<T>(w, a.H, a.R, wi);
-        if (a.attempted) {
-#pragma unroll
-            for (int t = 0; t < 6; ++t) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    att[t] += __shfl_down_sync(FULL, att[t], o);
-                    acc[t] += __shfl_down_sync(FULL, acc[t], o);
-                }
-                if (ln == 0) {
-                    atomicAdd(a.attempted + (size_t)k * 6 + t, (unsigned long long)att[t]);
-                    atomicAdd(a.accepted + (size_t)k * 6 + t, (unsigned long long)acc[t]);
-                }
-            }
+        if (a.attempted && threadIdx.x < 6) { // (the batch loop ends with a barrier)
+            atomicAdd(a.attempted + (size_t)k * 6 + threadIdx.x, (unsigned long long)cnt[threadIdx.x]);
+            atomicAdd(a.accepted + (size_t)k * 6 + threadIdx.x, (unsigned long long)cnt[6 + threadIdx.x]);
         }
         if (w.lane == 0) {
             if (!REPLAY) a.ctr[wi] = ctr0 + (unsigned long long)a.nmoves;
