@@ -310,10 +310,9 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
 }
 
 // W = 1: strictly one move at a time; W = 8: speculative windows of up to W moves.
-// MINB = resident one-warp CTAs per SM the register allocation must allow.  1: no cap (198 registers for hexamers: 8
-// walkers per SM) -- fastest while the batch fits the chip at once (1 024 walkers per GPU: 6.9 per SM); 16: 128 registers,
-// slower per walker (C3 -13 %, C2 -20 % at 1 024 walkers) but twice as many walkers in flight: C3 +7.5 %, C2 +15 % at
-// 4 096 walkers per GPU (A/B builds on B200).  The launcher picks by the size of the batch.
+// MINB = resident one-warp CTAs per SM the register allocation must allow.  1: no cap (214 - 221 registers: 9 walkers per
+// SM), fastest per walker; 12: 168 registers; 16: 128 registers -- slower per walker (C3 -15 % / -23 %, C2 -11 % / -22 % at
+// 1 024 walkers per GPU), more walkers in flight.  The launcher picks by the size of the batch (launch_lean).
 template <int NB, int W, bool REPLAY, int MINB>
 __global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
 {

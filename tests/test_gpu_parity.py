@@ -282,11 +282,13 @@ def test_mc_run_trajectory_bit_exact(eng, oracle, shape, tpw, sweeps):
     assert not pool.check_overlap().cpu().numpy().any()
 
 
-@pytest.mark.parametrize("shape", ["C1", "C2", "dimer"])
-def test_large_batch_uses_the_register_capped_kernel(eng, oracle, shape):
-    """More walkers than the uncapped warp-per-walker kernel keeps resident (8 per SM): the launcher switches to the
-    128-register build of the same kernel.  Same trajectories, bit for bit."""
-    nw, sweeps, seed = 1800, 1, 31337
+@pytest.mark.parametrize("shape,nw", [("C1", 1700), ("C2", 1800), ("dimer", 1700), ("C1", 2100)])
+def test_large_batch_uses_the_register_capped_kernel(eng, oracle, shape, nw):
+    """More walkers than the uncapped warp-per-walker kernel keeps resident (9 per SM): the launcher switches to a
+    register-capped build of the same kernel -- 168 registers for chains at 10 to 12 walkers per SM (1 700 on 148 SMs),
+    128 registers for single spheres -- and back to the uncapped one for chains beyond that (2 100).  Same trajectories,
+    bit for bit."""
+    sweeps, seed = 1, 31337
     cfg, H, R, k = make_walkers(shape, nw, seed=17, presweeps=0)
     pool = make_pool(eng, shape, H, R, k, seed=seed)
     limit = float(np.median([oracle.volume(H[w]) for w in range(0, nw, 50)]))
