@@ -27,6 +27,7 @@ import time
 
 import numpy as np
 
+_JSON_OUT = None  # the process's original stdout (set in main)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -232,7 +233,7 @@ def run_reference(args):
                           "one process per core"}
         except Exception as e:
             line["cpu_baseline"]["reference_shaped"] = {"value": None, "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -549,7 +550,7 @@ def run_b200(args):
             "dense_regime": dense,
             "other_workloads": others,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()
@@ -580,6 +581,12 @@ def main():
                     help="also time the MC_run-shaped Python loop (BASELINE.md variant i); on by default")
     ap.add_argument("--no-cpu-shaped", dest="cpu_shaped", action="store_false")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever native libraries print there while the bench runs
+    # (NCCL's "NCCL version ..." banner at communicator set-up) is sent to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
