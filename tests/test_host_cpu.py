@@ -356,3 +356,25 @@ def test_window_settle_rule_equals_serial_order():
             nwin += 1
         assert got == serial and np.array_equal(xw, xs)
         assert 0.2 < np.mean(serial) < 0.95 and nwin < len(moves) / min(W, 3) * 1.6
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exit 0, exactly ONE line on stdout, a
+    JSON object with the contract's keys and the same workload string the GPU arm reports for that workload."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mc_move_attempts_per_s" and d["unit"] == "moves/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"]["workload"].startswith("C3") and d["config"]["workload"] == bench.workload_string("C3", bench.WORKLOADS["C3"][3])
