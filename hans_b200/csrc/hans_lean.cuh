@@ -145,8 +145,16 @@ __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr
     const bool overlap = chain_overlaps_pruned<32, NB>(w, cr.f, ichain, b0, intra, Rt, pairs);
     if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
         const int P = W_P(w) + 3 * c0;
-        for (int k = w.lane; k < 3 * NB; k += 32) smem[P + k] = smem[cn + k];
-        for (int k = w.lane; k < NB; k += 32) SM4[f4 + c0 + k] = SM4[c4 + k];
+        {   // beads (3 NB doubles = 3 NB / 2 sixteen-byte words; P and cn are even) and shadows in one pass of 16-byte copies
+            constexpr int n2 = 3 * NB / 2;
+            static_assert(NB % 2 == 0 && n2 + NB <= 32, "one pass");
+            const int k = w.lane;
+            if (k < n2 + NB) {
+                const int src = k < n2 ? (cn >> 1) + k : c4 + (k - n2);
+                const int dst = k < n2 ? (P >> 1) + k : f4 + c0 + (k - n2);
+                SM4[dst] = SM4[src];
+            }
+        }
         if (intra && w.lane == 0) SMF[w.rad + ichain] = Rt;
     }
     __syncwarp();

@@ -69,6 +69,7 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
 #endif
     const float4 ct = SM4[c4 + m];
     bool ov = false, amb = false;
+    int seen = intra ? 1 : 0; // (warp-uniform) was any bead pair tested at all?  If not, the vote at the end is skipped
     // TEAM_WAVES waves of 32 chain spheres at a time (independent tests in flight), ONE compaction, one pass over
     // the beads of the survivors
 #pragma unroll 1
@@ -97,6 +98,7 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
         }
         __syncwarp();
         const int items = cnt * nb;
+        seen |= items;
 #if HANS_TEAM_BEAD_PRUNE
         // bead level, two steps: which beads of the near chains lie inside the trial chain's bounding sphere (+ sigma)
         // -- one test per bead; then (bead, trial bead) pairs of the survivors spread over the lanes
@@ -186,6 +188,7 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             pairs += 1u;
         }
         unsigned nm = __ballot_sync(FULL, nr);
+        seen |= (int)nm;
         while (nm) {
             const int bit = __ffs(nm) - 1;
             nm &= nm - 1u;
@@ -207,6 +210,7 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             if (bit >= 8) newb |= (o ? 1u : 0u) << jj; else oldb |= (o ? 1u : 0u) << jj;
         }
     }
+    if (seen == 0) return 0u; // nothing near (the usual case of a dilute walker), or no move for this warp
     return __reduce_or_sync(FULL, (ov ? 1u : 0u) | (amb ? 2u : 0u) | (oldb << 8) | (newb << 16));
 }
 
@@ -359,8 +363,18 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                 // ---- C: commit -----------------------------------------------------------------------
                 if (wid < ndone && ((committed >> wid) & 1u)) {
                     const int P = W_P(w) + 3 * nb * ichain, f4c = W_F4(w) + nb * ichain;
-                    for (int e = ln; e < 3 * nb; e += 32) smem[P + e] = smem[cnk + e];
-                    for (int e = ln; e < nb; e += 32) SM4[f4c + e] = SM4[c4k + e];
+                    if (NB && NB % 2 == 0 && 5 * NB / 2 <= 32) {
+                        // beads (3 NB doubles = 3 NB / 2 sixteen-byte words; P and cnk are even) and shadows: one pass
+                        constexpr int n2 = 3 * NB / 2;
+                        if (ln < n2 + NB) {
+                            const int src = ln < n2 ? (cnk >> 1) + ln : c4k + (ln - n2);
+                            const int dst = ln < n2 ? (P >> 1) + ln : f4c + (ln - n2);
+                            SM4[dst] = SM4[src];
+                        }
+                    } else {
+                        for (int e = ln; e < 3 * nb; e += 32) smem[P + e] = smem[cnk + e];
+                        for (int e = ln; e < nb; e += 32) SM4[f4c + e] = SM4[c4k + e];
+                    }
                     if (intra && ln == 0) SMF[w.rad + ichain] = Rt;
                 }
                 {
