@@ -90,9 +90,10 @@ __device__ __noinline__ DecP lean_move_chain_generic(WCtx w, int q)
 }
 
 // single spheres (NB == 1), translation: alk.alkane_translate_chain + accept/restore
-// (MCNS.py:323,371-380).  Returns 1 accepted / 0 overlap.
+// (MCNS.py:323,371-380).  Returns 1 accepted / 0 rejected.  u_ok = the proposal's u_acc < 1 (MCNS.py:372 with boltz = 1:
+// always true for generated proposals; decided when the record entered the ring).
 __device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRegs &cr, unsigned sb, int q, int ichain,
-                                                     unsigned &pairs)
+                                                     bool u_ok, unsigned &pairs)
 {
     const int N = w.N;
     const unsigned pa = sb + 64u * (unsigned)(w.ring + q);             // the proposal record
@@ -121,29 +122,31 @@ __device__ __forceinline__ int lean_translate_sphere(const WCtx &w, const CellRe
         __syncwarp();
         overlap = lean_recheck(w, ichain, 0, true, false);
     }
-    if (!overlap && (lds_f64(pa + 48) < 1.0)) { // MCNS.py:372 with boltz = 1 (u_acc)
+    const bool accept = !overlap && u_ok; // MCNS.py:372
+    if (accept) {
         if (w.lane == 0) {
             sts_f64(Pa, x); sts_f64(Pa + 8, y); sts_f64(Pa + 16, z);
             sts_f4(fa + 16u * (unsigned)ichain, cs);
         }
         __syncwarp();
     }
-    return overlap ? 0 : 1;
+    return accept ? 1 : 0;
 }
 
 // chains of NB beads: translate / rotate / dihedral; chain-level pruning, trial shadows in registers
 template <int NB>
 __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr, const PropRec *p, int ichain,
-                                               unsigned &pairs)
+                                               bool u_ok, unsigned &pairs)
 {
     const int c0 = ichain * NB, cn = W_CN(w), c4 = W_C4(w), f4 = W_F4(w);
     int b0 = 0;
     bool intra = false;
-    make_trial(w, p, w.lane, 32, cn, c4, b0, intra); // (proposal validated by the caller)
+    make_trial(w, p, w.lane, 32, cn, c4, b0, intra, cr.Hi); // (proposal validated by the caller)
     __syncwarp();
     const float Rt = intra ? chain_radius_warp(cn, NB) : SMF[w.rad + ichain]; // translations and rotations are rigid
     const bool overlap = chain_overlaps_pruned<32, NB>(w, cr.f, ichain, b0, intra, Rt, pairs);
-    if (!overlap && (p->u_acc < 1.0)) { // MCNS.py:372 with boltz = 1
+    const bool accept = !overlap && u_ok; // MCNS.py:372 with boltz = 1
+    if (accept) {
         const int P = W_P(w) + 3 * c0;
         {   // beads (3 NB doubles = 3 NB / 2 sixteen-byte words; P and cn are even) and shadows in one pass of 16-byte copies
             constexpr int n2 = 3 * NB / 2;
@@ -158,7 +161,7 @@ __device__ __forceinline__ int lean_move_chain(const WCtx &w, const CellRegs &cr
         if (intra && w.lane == 0) SMF[w.rad + ichain] = Rt;
     }
     __syncwarp();
-    return overlap ? 0 : 1;
+    return accept ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,8 +276,8 @@ __device__ __forceinline__ int lean_window(const WCtx &w, const CellRegs &cr, in
             __syncwarp();
             if (lean_recheck(w, ci, b0i, true, pi->type == HANS_DIH)) continue;
         }
+        if (!(pi->u_acc < 1.0)) continue; // MCNS.py:372 with boltz = 1 (only explicit proposals can fail it): rejected
         accbits |= 1u << i;
-        if (!(pi->u_acc < 1.0)) continue; // MCNS.py:372 with boltz = 1 (only explicit proposals can fail it)
         {
             const int P = W_P(w) + 3 * NB * ci, f4c = f4 + NB * ci;
             for (int e = lane; e < 3 * NB; e += 32) smem[P + e] = smem[wci + e];
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
             const int nbatch = a.nmoves - m0 < T ? a.nmoves - m0 : T;
             int my_type = -1;
             bool my_plain = false; // a single-chain move with a well-formed proposal
+            bool my_uok = false;   // u_acc < 1: an accepted single-chain move commits (MCNS.py:372 with boltz = 1)
             if (w.lane < nbatch) {
                 PropRec *slot = ring + w.lane;
                 if (REPLAY) {
@@ -357,12 +361,14 @@ __global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
                     my_type = pr.type;
                 }
                 prep_slot(slot);
+                my_uok = slot->u_acc < 1.0;
                 my_plain = (my_type == HANS_TRANS || (NB > 1 && my_type == HANS_ROT) ||
                             (my_type == HANS_DIH && NB >= 4 && slot->idx0 >= 3 && slot->idx0 <= NB - 1)) &&
                            (unsigned)slot->ichain < (unsigned)w.nc;
             }
             __syncwarp();
             const unsigned plain = W > 1 ? __ballot_sync(FULL, my_plain) : 0u;
+            const unsigned uok = __ballot_sync(FULL, my_uok);
             // decisions of the batch: accepted bits (uniform); reason / boltz of the moves that are not
             // plain single-chain moves are kept by lane q (a chain move's follow from its bit)
             unsigned accmask = 0;
@@ -392,10 +398,10 @@ __global__ void __launch_bounds__(32, MINB) walk_lean_kernel(const WalkArgs a)
                 }
                 const bool chain_ok = (unsigned)ichain < (unsigned)w.nc;
                 if (NB == 1 && type == HANS_TRANS && chain_ok) {
-                    accmask |= (unsigned)lean_translate_sphere(w, cr, sb, q, ichain, pairs) << q;
+                    accmask |= (unsigned)lean_translate_sphere(w, cr, sb, q, ichain, ((uok >> q) & 1u) != 0u, pairs) << q;
                 } else if (NB > 1 && chain_ok &&
                            (type == HANS_TRANS || type == HANS_ROT || (type == HANS_DIH && NB >= 4 && idx0 >= 3 && idx0 <= NB - 1))) {
-                    accmask |= (unsigned)lean_move_chain<(NB > 1 ? NB : 2)>(w, cr, p, ichain, pairs) << q;
+                    accmask |= (unsigned)lean_move_chain<(NB > 1 ? NB : 2)>(w, cr, p, ichain, ((uok >> q) & 1u) != 0u, pairs) << q;
                 } else {
                     DecP d;
                     if (type >= HANS_TRANS && type <= HANS_DIH) {

@@ -69,7 +69,6 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
 #endif
     const float4 ct = SM4[c4 + m];
     bool ov = false, amb = false;
-    int seen = intra ? 1 : 0; // (warp-uniform) was any bead pair tested at all?  If not, the vote at the end is skipped
     // TEAM_WAVES waves of 32 chain spheres at a time (independent tests in flight), ONE compaction, one pass over
     // the beads of the survivors
 #pragma unroll 1
@@ -98,7 +97,6 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
         }
         __syncwarp();
         const int items = cnt * nb;
-        seen |= items;
 #if HANS_TEAM_BEAD_PRUNE
         // bead level, two steps: which beads of the near chains lie inside the trial chain's bounding sphere (+ sigma)
         // -- one test per bead; then (bead, trial bead) pairs of the survivors spread over the lanes
@@ -188,7 +186,6 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             pairs += 1u;
         }
         unsigned nm = __ballot_sync(FULL, nr);
-        seen |= (int)nm;
         while (nm) {
             const int bit = __ffs(nm) - 1;
             nm &= nm - 1u;
@@ -210,7 +207,6 @@ __device__ __forceinline__ unsigned team_test(const WCtx &w, const Filt &f, cons
             if (bit >= 8) newb |= (o ? 1u : 0u) << jj; else oldb |= (o ? 1u : 0u) << jj;
         }
     }
-    if (seen == 0) return 0u; // nothing near (the usual case of a dilute walker), or no move for this warp
     return __reduce_or_sync(FULL, (ov ? 1u : 0u) | (amb ? 2u : 0u) | (oldb << 8) | (newb << 16));
 }
 
@@ -380,7 +376,7 @@ __global__ void __launch_bounds__(32 * NWARP, 16 / NWARP) walk_team_kernel(const
                 {
                     const int d = w.lane - q;
                     if (d >= 0 && d < ndone) {
-                        my_acc = (int)((accepted >> d) & 1u);
+                        my_acc = (int)((committed >> d) & 1u); // accepted = no overlap AND u_acc < 1 (MCNS.py:372)
                         my_reason = my_acc ? HANS_ACCEPT : HANS_REJ_OVERLAP;
                         my_boltz = my_acc ? 1.0 : 0.0;
                     }

@@ -224,6 +224,29 @@ def test_replay_band_hits(eng, oracle, tpw):
     assert _lib.diag_counters()[0] >= nw * 10  # the float64 settle really ran
 
 
+@pytest.mark.parametrize("shape,tpw", [("dimer", 0), ("dimer", 8), ("dimer", 32), ("C2", 0), ("C2", 8), ("C1", 0), ("C1", 24),
+                                       ("C4s", 28), ("C4s", 128)])
+def test_replay_u_acc_at_or_above_one_is_a_rejection(eng, oracle, shape, tpw):
+    """MCNS.py:372 accepts a single-chain move iff U < boltz, boltz = 1 without overlap.  Generated U lie in [0, 1); an
+    EXPLICIT proposal may carry U >= 1: the move is then rejected (not accepted-but-uncommitted) in every kernel family,
+    as in the oracle."""
+    nw, nmoves = 5, 48
+    cfg, H, R, k = make_walkers(shape, nw, seed=41)
+    props = np.stack([oracle.gen_proposals(cfg, 4242, w, 0, nmoves) for w in range(nw)])
+    props["u_acc"][:, ::3] = 1.0
+    props["u_acc"][:, 1::6] = 1.5
+    H0, R0 = H.copy(), R.copy()
+    want = np.stack([oracle.replay(cfg, H[w], R[w], props[w], 1e300, 0) for w in range(nw)])  # (advances H, R)
+    chain_moves = (props["type"] >= 1) & (props["type"] <= 3)
+    assert not want["accepted"][chain_moves & (props["u_acc"] >= 1.0)].any()
+    assert want["accepted"][chain_moves & (props["u_acc"] < 1.0)].any()
+    pool = make_pool(eng, shape, H0, R0, k, tpw=tpw)
+    got = pool.replay(None, props, volume_limit=1e300, mode=0)
+    for f in ("accepted", "reason"):
+        assert np.array_equal(got[f], want[f]), f
+    assert_state_equal(pool, H, R)
+
+
 def test_replay_propose_mode(eng, oracle):
     """hs_alkane entry-point semantics: trial state left in place, boltz returned."""
     _replay_case(eng, oracle, "C1", 32, nwalkers=6, nmoves=60, mode=1)
