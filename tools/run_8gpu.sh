@@ -12,8 +12,8 @@ run() { # name nproc extra-env args...
 }
 # what to run: "$1" = n8 (default), peer, n4, n2 -- one gpurun call each, so that a call only pays for the GPUs it uses
 case "${1:-n8}" in
-n8)   run r02f_bench_c3_n8_nccl 8 HANS_NS_PEER=0 --others C4,C5 ;;
-peer) run r02f_bench_c3_n8_peer 8 HANS_NS_PEER=1 --others "" ;;
-n4)   run r02f_bench_c3_strong_n4 4 HANS_NS_PEER=0 --total-walkers 8192 --others "" ;;
-n2)   run r02f_bench_c3_strong_n2 2 HANS_NS_PEER=0 --total-walkers 8192 --others "" ;;
+n8)   run r02g_bench_c3_n8_nccl 8 HANS_NS_PEER=0 --others C4,C5 ;;
+peer) run r02g_bench_c3_n8_peer 8 HANS_NS_PEER=1 --others "" ;;
+n4)   run r02g_bench_c3_strong_n4 4 HANS_NS_PEER=0 --total-walkers 8192 --others "" ;;
+n2)   run r02g_bench_c3_strong_n2 2 HANS_NS_PEER=0 --total-walkers 8192 --others "" ;;
 esac
