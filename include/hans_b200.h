@@ -88,8 +88,11 @@ typedef struct hans_proposal {
     int32_t idx0; /* dih: first rotated bead | shear: k | stretch: i */
     int32_t idx1; /* dih: flip | stretch: j */
     double p[4];  /* vol: dV | trans: dr[3] | rot: quaternion wxyz | dih: angle | shear: rv1,rv2 |
-                     stretch: rv */
-    double u_acc;
+                     stretch: rv.  (Fields a move type does not use are ignored on input; the walk kernels use p[1], p[2] of
+                     their shared-memory copy of a dihedral record for sin / cos of the half angle.) */
+    double u_acc; /* the uniform draw of MCNS.py:351,372: accepted iff u_acc < boltz.  Generated values lie in [0, 1); an
+                     explicit value >= 1 makes a single-chain move a rejection (reason HANS_REJ_OVERLAP, as the reference's
+                     else-branch would report it) */
     double reserved;
 } hans_proposal;
 
