@@ -468,12 +468,16 @@ template <bool REPLAY> static int launch_lean(const WalkArgs &a, int W, cudaStre
         walk_lean_kernel<NN, WW, REPLAY, MB><<<spec_grid(a.n_active), 32, smem, st>>>(a);     \
     })
     // Register allocation by the size of the batch (one-warp CTAs; A/B builds on B200, M moves/s).
-    // Uncapped (214 - 221 registers: 9 walkers per SM) is fastest per walker and, for chains, also in total at any batch
-    // size but one: a batch of 9 to 12 walkers per SM leaves a short second wave, and the 168-register build (12 per SM)
-    // takes it at once (C3, 1 536 walkers: 608 vs 490).  Single spheres lose less to the cap: beyond 9 walkers per SM the
+    // Uncapped (214 - 243 registers: 8 or 9 walkers per SM) is fastest per walker and, for chains, also in total at any batch
+    // size but one: a batch of more than that and up to 12 walkers per SM leaves a short second wave, and the 168-register build (12 per SM)
+    // takes it at once (C3, 1 536 walkers: 608 vs 490).  Single spheres lose less to the cap: beyond what the uncapped build holds the
     // 128-register build (16 per SM) wins (C2, 2 048 / 4 096 walkers: 1 876 / 2 046 vs 1 727 / 1 800).
     const int per_sm = (a.n_active + sm_count() - 1) / sm_count();
-    const int mb = per_sm <= 9 ? 1 : c->nbeads == 1 ? 16 : per_sm <= 12 ? 12 : 1;
+    int fit = 8; // one-warp CTAs of the uncapped build an SM holds (registers, shared memory): asked of the runtime
+    if (W == 1) {
+        DISPATCH_NB(c->nbeads, { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, walk_lean_kernel<NN, 1, REPLAY, 1>, 32, smem) != cudaSuccess || fit < 1) { (void)cudaGetLastError(); fit = 8; } })
+    }
+    const int mb = per_sm <= fit ? 1 : c->nbeads == 1 ? 16 : per_sm <= 12 ? 12 : 1;
     if (W == 1) { if (mb == 16) { LEAN_LAUNCH(1, 16); } else if (mb == 12) { LEAN_LAUNCH(1, 12); } else { LEAN_LAUNCH(1, 1); } }
     else { LEAN_LAUNCH(8, 1); }
 #undef LEAN_LAUNCH

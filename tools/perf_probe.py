@@ -7,6 +7,7 @@ from hans_b200 import engine
 CASES = {
     "C2": (64, 1, [1, 192, 0, 0, 3, 3], 1024),
     "C3_1024": (16, 6, [3, 48, 32, 0, 3, 3], 1024),
+    "C3_1300": (16, 6, [3, 48, 32, 0, 3, 3], 1300),
     "C3_1536": (16, 6, [3, 48, 32, 0, 3, 3], 1536),
     "C3_2048": (16, 6, [3, 48, 32, 0, 3, 3], 2048),
     "C2_2048": (64, 1, [1, 192, 0, 0, 3, 3], 2048),
