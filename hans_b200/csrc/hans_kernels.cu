@@ -721,6 +721,7 @@ static WsPlan ws_plan(int n_active, int total, bool have_ws, uint64_t workspace_
 
 int hans_mc_run_launches(int n_active, int nmoves, int have_workspace, uint64_t workspace_bytes)
 {
+    if (n_active <= 0 || nmoves <= 0) return 0; // nothing is launched for an empty batch
     const WsPlan p = ws_plan(n_active, nmoves, have_workspace != 0, workspace_bytes);
     return p.nchunks ? 2 * p.nchunks : 1;
 }

@@ -100,6 +100,36 @@ def test_host_side_entry_points_and_validation():
     assert L.hans_device_count() >= 0
 
 
+def test_empty_inputs_are_no_ops_and_negative_counts_are_errors():
+    """Zero walkers / zero moves: every batched entry point returns HANS_OK before it touches the device (so this runs
+    without a GPU; the pointers are never dereferenced); a negative count is HANS_EINVAL."""
+    from hans_b200 import _lib
+    L = _lib.lib
+    cfg = _lib.make_cfg(16, 6, [3, 48, 32, 0, 3, 3])
+    c, p = C.byref(cfg), C.c_void_p(4096)   # any non-NULL "device pointer"
+    assert L.hans_mc_run_batch_ws(c, p, p, p, None, 0, 40, None, 1e300, 1, 0, None, None, None, None, 0, None, 0, None) == 0
+    assert L.hans_mc_run_batch(c, p, p, p, None, 0, 40, None, 1e300, 1, 0, None, None, None, None, 0, None) == 0
+    assert L.hans_gen_proposals(c, p, None, 0, 87, 1, 0, p, None) == 0 and L.hans_gen_proposals(c, p, None, 5, 0, 1, 0, p, None) == 0
+    assert L.hans_replay(c, p, p, None, 0, p, 10, 1e300, 0, p, 0, None) == 0 and L.hans_replay(c, p, p, None, 3, p, 0, 1e300, 0, p, 0, None) == 0
+    assert L.hans_check_overlap(c, p, p, None, 0, 0, p, 0, None) == 0
+    assert L.hans_cell_metrics(p, 0, p, p, p, None) == 0
+    assert L.hans_change_box(c, p, p, None, 0, p, None) == 0
+    assert L.hans_shape_delta(p, None, 0, p, p, None) == 0
+    assert L.hans_grow(c, p, p, 0, 1, 0, 10, None, None) == 0
+    assert L.hans_order_params(c, p, p, 0, p, p, None) == 0
+    assert L.hans_mc_run_launches(0, 3480, 1, 1 << 30) == 0
+    for rc in (L.hans_mc_run_batch_ws(c, p, p, p, None, -1, 40, None, 1e300, 1, 0, None, None, None, None, 0, None, 0, None),
+               L.hans_mc_run_batch_ws(c, p, p, p, None, 4, -1, None, 1e300, 1, 0, None, None, None, None, 0, None, 0, None),
+               L.hans_gen_proposals(c, p, None, -1, 1, 1, 0, p, None), L.hans_replay(c, p, p, None, -2, p, 1, 1e300, 0, p, 0, None),
+               L.hans_check_overlap(c, p, p, None, -1, 0, p, 0, None), L.hans_cell_metrics(p, -1, p, p, p, None),
+               L.hans_change_box(c, p, p, None, -1, p, None), L.hans_shape_delta(p, None, -1, p, p, None),
+               L.hans_grow(c, p, p, -1, 1, 0, 10, None, None), L.hans_grow(c, p, p, 0, 1, 0, 0, None, None),
+               L.hans_order_params(c, p, p, -1, p, p, None)):
+        assert rc == -1, L.hans_last_error()
+    # attempted / accepted counters go together (checked before the early return)
+    assert L.hans_mc_run_batch_ws(c, p, p, p, None, 0, 40, None, 1e300, 1, 0, p, None, None, None, 0, None, 0, None) == -1
+
+
 def test_no_product_module_touches_the_oracle():
     """The product path must not import, link, open or execute anything under oracle/ (nor the test harness)."""
     import ast
