@@ -640,9 +640,6 @@ static int launch_coop(const hans_cfg *cfg, const WalkArgs &a, bool from_memory,
     return HANS_OK;
 }
 
-// does the cell-list kernel fit shared memory for this shape (with T threads per walker)?
-static bool cells_fit(const hans_cfg *cfg, int T) { return cta_smem_bytes(cfg, T, true) <= 227 * 1024; }
-
 static int launch_walk(const hans_cfg *cfg, WalkArgs &a, bool from_memory, int threads_per_walker, cudaStream_t st)
 {
     const bool want_cells = (threads_per_walker & HANS_TPW_CELLS) != 0;
