@@ -197,3 +197,21 @@ def test_peer_exchange_buffer_size():
     assert L.hans_ns_peer_bytes(768, 2) == 8 * (16 + 2 * 2 * (12 + 2304))
     assert L.hans_ns_peer_bytes(64, 16) == 8 * (32 + 2 * 16 * (12 + 192))
     assert L.hans_ns_peer_bytes(0, 2) == 0
+
+
+def test_product_fails_loudly_without_extension_or_gpu():
+    """No CPU fallback anywhere on the product path: a missing library is an ImportError that says so; without a CUDA
+    device the walker pool refuses to exist; the GPU arm of bench.py exits non-zero instead of measuring something else."""
+    import subprocess
+    import sys
+    env = dict(os.environ, HANS_B200_LIB=os.path.join(ROOT, "does", "not", "exist.so"))
+    r = subprocess.run([sys.executable, "-c", "import hans_b200._lib"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert r.returncode != 0 and "ImportError" in r.stderr and "no CPU fallback" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        from hans_b200 import _lib, engine
+        with pytest.raises(_lib.HansError, match="no CPU fallback"):
+            engine.WalkerPool(4, 16, 6, [3, 48, 32, 0, 3, 3])
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu"],
+                           capture_output=True, text=True, cwd=ROOT, timeout=600)
+        assert r.returncode != 0 and not r.stdout.strip().startswith("{"), (r.returncode, r.stdout[:200])
